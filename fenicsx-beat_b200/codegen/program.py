@@ -1,0 +1,195 @@
+"""Time-stepping schemes over an :class:`OdeModel` -> a scheduled straight-line program.
+
+Schemes
+-------
+``forward_explicit_euler``   y_new = y + dt*f                       (README.md:58-89 of the reference
+                             writes the same update by hand for FitzHugh-Nagumo)
+``generalized_rush_larsen``  first-order generalized Rush-Larsen (GRL1) as gotranx emits it for the
+                             reference's demos (demos/niederer_benchmark.py:82-98): for each state y
+                             with written right-hand side f,
+                                 lin = d f / d y   (intermediates held fixed)
+                                 lin == 0          -> y + dt*f
+                                 otherwise         -> y + f*(exp(lin*dt) - 1)/lin,
+                                                      guarded by |lin| > 1e-8 (else dt*f) unless lin is a
+                                                      fraction with a non-zero constant numerator.
+                             gotranx itself is not installable here, so this is a
+                             restatement of its published scheme: parity at that boundary is unpinned.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+from . import ir
+from .odefile import OdeModel
+
+SCHEMES = ("forward_explicit_euler", "generalized_rush_larsen")
+RL_DELTA = 1e-8
+
+
+@dataclass
+class Program:
+    model: OdeModel
+    scheme: str
+    uniform: list[tuple[str, ir.Node]] = field(default_factory=list)  # parameter-only, topo order
+    body: list[tuple[str, ir.Node]] = field(default_factory=list)  # node-dependent, topo order
+    outputs: list[ir.Node] = field(default_factory=list)  # one per state, index order
+    rl_states: list[str] = field(default_factory=list)
+    fe_states: list[str] = field(default_factory=list)
+
+    @property
+    def used_parameters(self) -> list[str]:
+        used: set[str] = set()
+        for _, e in self.uniform + self.body:
+            used |= ir.free_symbols(e)
+        for e in self.outputs:
+            used |= ir.free_symbols(e)
+        return [p for p in self.model.parameters if p in used]
+
+
+def build_program(model: OdeModel, scheme: str) -> Program:
+    if scheme not in SCHEMES:
+        raise ValueError(f"unknown scheme {scheme!r}; have {SCHEMES}")
+    prog = Program(model=model, scheme=scheme)
+    dt = ir.sym("dt")
+    defs: dict[str, ir.Node] = dict(model.intermediates)
+    roots: list[str] = []
+    for s in model.states:
+        dname = f"d{s}_dt"
+        f = model.derivatives[s]
+        defs[dname] = f
+        fsym = ir.sym(dname)
+        y = ir.sym(s)
+        if scheme == "forward_explicit_euler":
+            prog.outputs.append(ir.add(y, ir.mul(dt, fsym)))
+            prog.fe_states.append(s)
+            roots.append(dname)
+            continue
+        lin = ir.diff(f, s)
+        if ir.is_num(lin, 0.0):
+            prog.outputs.append(ir.add(y, ir.mul(dt, fsym)))
+            prog.fe_states.append(s)
+            roots.append(dname)
+            continue
+        lname = f"{dname}_linearized"
+        defs[lname] = lin
+        lsym = ir.sym(lname)
+        rl = ir.div(ir.mul(fsym, ir.sub(ir.call("exp", ir.mul(lsym, dt)), ir.ONE)), lsym)
+        if not ir.numerator_is_nonzero_constant(lin):
+            rl = ir.cond(ir.cmp("gt", ir.call("abs", lsym), ir.num(RL_DELTA)), rl, ir.mul(dt, fsym))
+        prog.outputs.append(ir.add(y, rl))
+        prog.rl_states.append(s)
+        roots += [dname, lname]
+
+    # ---- dependency-ordered schedule, dead code dropped -------------------------
+    params = set(model.parameters)
+    order: list[str] = []
+    state = {}  # name -> 0 visiting / 1 done
+
+    def visit(name: str) -> None:
+        st = state.get(name)
+        if st == 1:
+            return
+        if st == 0:
+            raise ValueError(f"cyclic definition through {name}")
+        state[name] = 0
+        for dep in sorted(ir.free_symbols(defs[name])):
+            if dep in defs:
+                visit(dep)
+        state[name] = 1
+        order.append(name)
+
+    # visit in source order so the schedule is stable and readable
+    needed: set[str] = set()
+    stack = list(roots)
+    while stack:
+        n = stack.pop()
+        if n in needed:
+            continue
+        needed.add(n)
+        stack += [d for d in ir.free_symbols(defs[n]) if d in defs]
+    for name in defs:
+        if name in needed:
+            visit(name)
+
+    uniform_names: set[str] = set()
+    for name in order:
+        deps = ir.free_symbols(defs[name])
+        if all((d in params) or (d in uniform_names) for d in deps):
+            uniform_names.add(name)
+            prog.uniform.append((name, defs[name]))
+        else:
+            prog.body.append((name, defs[name]))
+
+    # ---- hoist maximal parameter-only sub-expressions out of the node-dependent part ----------
+    # (e.g. R*T/F, sqrt(K_o/5.4) in TP06): evaluated once on the host per parameter set, or once per
+    # thread when parameters are per-node.  Evaluation order inside the hoisted tree is unchanged.
+    fs_memo: dict = {}
+    hoisted: dict[int, ir.Node] = {}
+
+    def leaf_map(x: ir.Node):
+        if x.kind in ("num", "sym"):
+            return None
+        if x.kind in ("lt", "gt", "le", "ge", "eq", "ne", "and", "or"):
+            return None  # booleans are not stored as doubles
+        syms = ir.free_symbols(x, fs_memo)
+        if syms and all((s in params) or (s in uniform_names) for s in syms):
+            h = hoisted.get(id(x))
+            if h is None:
+                name = f"_u{len(hoisted)}"
+                h = ir.sym(name)
+                hoisted[id(x)] = h
+                prog.uniform.append((name, x))
+                uniform_names.add(name)
+            return h
+        return None
+
+    memo: dict = {}
+    prog.body = [(n, ir.rebuild(e, leaf_map, memo)) for n, e in prog.body]
+    prog.outputs = [ir.rebuild(e, leaf_map, memo) for e in prog.outputs]
+    return prog
+
+
+def op_counts(prog: Program, include_uniform: bool = False) -> dict[str, int]:
+    """Arithmetic per node-step after common-subexpression sharing (the DAG is hash-consed, so each
+    distinct node is counted once).  Used for the fp64 roofline in DESIGN.md / bench.py."""
+    seen: set[int] = set()
+    counts = {k: 0 for k in ("add", "mul", "div", "exp", "log", "sqrt", "pow", "floor", "abs", "cmp", "select", "neg")}
+
+    def rec(x: ir.Node) -> None:
+        if id(x) in seen:
+            return
+        seen.add(id(x))
+        for a in x.args:
+            rec(a)
+        k = x.kind
+        if k in ("add", "sub"):
+            counts["add"] += 1
+        elif k == "mul":
+            counts["mul"] += 1
+        elif k == "div":
+            counts["div"] += 1
+        elif k == "neg":
+            counts["neg"] += 1
+        elif k == "pow":
+            b = x.args[1]
+            if ir.is_num(b) and float(b.value).is_integer() and 2 <= abs(b.value) <= 16:
+                n = int(abs(b.value))
+                counts["mul"] += n.bit_length() - 1 + bin(n).count("1") - 1
+                if b.value < 0:
+                    counts["div"] += 1
+            else:
+                counts["pow"] += 1
+        elif k == "call":
+            counts[x.value] += 1
+        elif k == "cond":
+            counts["select"] += 1
+        elif k in ("lt", "gt", "le", "ge", "eq", "ne", "and", "or"):
+            counts["cmp"] += 1
+
+    exprs = [e for _, e in prog.body] + list(prog.outputs)
+    if include_uniform:
+        exprs += [e for _, e in prog.uniform]
+    for e in exprs:
+        rec(e)
+    return counts

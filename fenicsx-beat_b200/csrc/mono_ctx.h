@@ -1,0 +1,145 @@
+// Internal state behind the opaque mono_ctx of include/mono_abi.h.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mono_abi.h"
+
+struct ncclComm;
+
+// one stimulus as the device sees it (array of these lives in device memory)
+struct StimDev {
+  int64_t nnz;
+  const int32_t* idx;
+  const double* val;
+  double t_start, t_end, amp;
+};
+
+// result block written by the PDE kernel (device memory, read back on demand)
+struct KspResult {
+  int iterations;
+  int reason;
+  double rnorm;
+  long long total_iterations;
+  long long solves;
+  int error;  // non-zero: kernel-side failure (e.g. barrier timeout)
+};
+
+struct ProbeDev {
+  int n;           // nodes in this probe (<= 4)
+  int32_t node[4];
+  double w[4];
+};
+
+struct mono_ctx {
+  int device = -1;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // ---- comm -------------------------------------------------------------------------------
+  int nranks = 1, rank = 0;
+  ncclComm* comm = nullptr;
+  int n_nbr = 0;
+  std::vector<int32_t> nbr_ranks, send_ptr, recv_ptr;
+  int32_t* send_idx_dev = nullptr;  // concatenated owned indices to pack
+  double* send_buf = nullptr;       // packed values, one segment per neighbour
+  int64_t n_send = 0;
+  double* red_buf = nullptr;        // scalars for all-reduce (device)
+
+  // ---- ODE ----------------------------------------------------------------------------------
+  bool has_ode = false;
+  int model_id = -1, scheme_id = -1, ns = 0, np = 0, nd = 0, v_index = 0;
+  int64_t npts = 0, ld = 0;
+  double* states = nullptr;  // ns x ld (row = state, SoA)
+  double* v_ode = nullptr;   // npts
+  bool per_node = false;
+  double* params_dev = nullptr;  // np x ld when per_node
+  std::vector<double> params_host;  // np shared parameters followed by nd derived constants
+  bool have_params = false;
+
+  // ---- PDE ----------------------------------------------------------------------------------
+  bool has_pde = false;
+  int64_t n_owned = 0, n_ghost = 0, n_local = 0;
+  int64_t n_slices = 0, sell_nnz = 0;   // SELL-32 storage
+  int64_t* slice_ptr = nullptr;          // n_slices+1 element offsets
+  int32_t* cols = nullptr;               // sell_nnz
+  double *mass = nullptr, *stiff = nullptr, *A = nullptr, *B = nullptr;  // sell_nnz each
+  double* dinv = nullptr;                // 1/diag(A) (or 1 for PC none), n_owned
+  double *x = nullptr, *v_prev = nullptr, *b = nullptr, *r = nullptr, *z = nullptr, *p0 = nullptr,
+         *p1 = nullptr, *q = nullptr;  // vectors of n_local (x, v_prev, z, p*) or n_owned
+  double C_m = 1.0, theta = 0.5, rtol = 1e-5, atol = 1e-50;
+  int max_it = 10000, pc_type = MONO_PC_JACOBI, norm_type = MONO_NORM_PRECONDITIONED, x0_mode = MONO_X0_ZERO;
+  double cur_dt = -1.0;
+  bool have_dt = false;
+  std::vector<StimDev> stims_host;
+  std::vector<void*> stim_allocs;
+  StimDev* stims_dev = nullptr;
+  int stims_dev_cap = 0;
+  bool stims_dirty = true;
+
+  // grid-barrier + reduction scratch for the persistent PDE kernel
+  unsigned* bar = nullptr;      // [0]=count [1]=generation
+  double* partials = nullptr;   // 2 parities x 4 scalars x max_blocks
+  int pde_blocks = 0, pde_threads = 0;
+  KspResult* ksp_dev = nullptr;
+  KspResult* ksp_host = nullptr;  // pinned
+
+  // fused-step bookkeeping: after mono_split_step the solution x is authoritative and
+  // states[v_index], v_ode, v_prev are refreshed lazily (canonicalize()).
+  bool fused_pending = false;
+
+  // ---- observers ------------------------------------------------------------------------------
+  std::vector<ProbeDev> probes_host;
+  ProbeDev* probes_dev = nullptr;
+  double* probe_vals_dev = nullptr;
+  double* probe_act_dev = nullptr;
+  bool probes_dirty = true;
+  bool act_enabled = false;
+  double act_threshold = 0.0;
+
+  // ---- measurement ---------------------------------------------------------------------------
+  cudaEvent_t timers[8][2] = {};
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  bool stage_timing = false;
+  std::vector<cudaEvent_t> ev_pool;  // [ode_start, ode_stop, pde_start, pde_stop] per recorded step
+  size_t ev_used = 0;
+  std::vector<int> ev_tags;          // stage (0 = ode, 1 = pde) of each recorded event pair
+  double stage_ms[2] = {0, 0};
+  int64_t stage_steps = 0;
+};
+
+// ---- helpers shared by the translation units ---------------------------------------------------
+int mono_fail(mono_ctx* c, int code, const std::string& msg);
+#define MONO_CUDA(c, call)                                                                          \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return mono_fail((c), MONO_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+#define MONO_CHECK(c, cond, msg)                          \
+  do {                                                    \
+    if (!(cond)) return mono_fail((c), MONO_E_INVALID, (msg)); \
+  } while (0)
+
+// ode_kernels.cu
+int ode_model_dims(int model_id, int* ns, int* np);
+int ode_model_num_derived(int model_id, int scheme_id);
+// launches the cell-model kernel over [0, n): V is read from v_in when non-null (else from the
+// states row), new V additionally written to v_out1 / v_out2 when non-null.
+int ode_launch(mono_ctx* c, double t, double dt, const double* v_in, double* v_out1, double* v_out2);
+
+// pde_kernels.cu
+int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, const double* mass, const double* stiff);
+int pde_update_matrices(mono_ctx* c, double dt);
+int pde_launch_step(mono_ctx* c, double t_eval, double dt);
+int pde_setup_launch_config(mono_ctx* c);
+int probes_launch(mono_ctx* c, double t0);
+
+// halo.cu
+int halo_refresh(mono_ctx* c, double* vec);  // owner -> ghost copy of an n_local vector (no-op for 1 rank)

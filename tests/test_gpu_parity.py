@@ -1,0 +1,187 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run on a B200: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): one ODE step <= 1e-12 relative in fp64; one PDE step <= 1e-8
+relative at matched (tight) solver tolerance.
+"""
+import numpy as np
+import pytest
+
+import _problems as P
+from oracle import monodomain as om_mono
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    """max over states of  max_i |a-b| / max(|b_i|, 1e-6 * max_row|b|)  - element-wise relative error with
+    a floor that keeps exact zeros / denormal gates (e.g. TP06 r ~ 1e-8) from dividing by nothing."""
+    scale = np.maximum(np.abs(b), 1e-6 * np.abs(b).max(axis=1, keepdims=True) + 1e-300)
+    return float((np.abs(a - b) / scale).max())
+
+
+@pytest.mark.parametrize("tag", ["fhn", "tp06", "torord"])
+@pytest.mark.parametrize("scheme", ["forward_explicit_euler", "generalized_rush_larsen"])
+@pytest.mark.parametrize("n", [1, 31, 20000])
+def test_ode_single_step(ctx_factory, tag, scheme, n):
+    import importlib
+
+    om = P.oracle_model(tag)
+    hm = importlib.import_module(f"beat_b200.models.{tag}")
+    rng = np.random.default_rng(1234)
+    states = P.perturbed_states(om, n, rng, P.V_NAME[tag])
+    params = om.init_parameter_values()
+    dev = getattr(hm, scheme)
+    ctx = ctx_factory()
+    ctx.ode_create(P.MODEL_ID[tag], P.SCHEME_ID[scheme], n, om.state_index(P.V_NAME[tag]), states.shape[0])
+    ctx.ode_set_states(states)
+    ctx.ode_set_params(params, dev.derived(params))
+    for t0 in (0.0, 10.5):
+        ctx.ode_set_states(states)
+        ctx.ode_step(t0, 0.01)
+        got = ctx.ode_get_states()
+        with np.errstate(all="ignore"):
+            want = getattr(om, scheme)(states, t0, 0.01, params)
+        assert np.isfinite(got).all()
+        err = rel_err(got, want)
+        assert err <= 1e-12, f"{tag}/{scheme} n={n} t={t0}: rel err {err:.3e}"
+    ctx.close()
+
+
+@pytest.mark.parametrize("tag", ["tp06"])
+def test_ode_per_node_parameters(ctx_factory, tag):
+    om = P.oracle_model(tag)
+    rng = np.random.default_rng(7)
+    n = 4097
+    states = P.perturbed_states(om, n, rng, P.V_NAME[tag])
+    p0 = om.init_parameter_values()
+    params = np.repeat(p0[:, None], n, axis=1) * (1 + 0.05 * rng.uniform(-1, 1, (len(p0), n)))
+    ctx = ctx_factory()
+    ctx.ode_create(P.MODEL_ID[tag], 1, n, om.state_index("V"), states.shape[0])
+    ctx.ode_set_states(states)
+    ctx.ode_set_params(params)
+    ctx.ode_step(3.0, 0.01)
+    got = ctx.ode_get_states()
+    want = om.generalized_rush_larsen(states, 3.0, 0.01, params)
+    assert rel_err(got, want) <= 1e-12
+    ctx.close()
+
+
+def _pde_ctx(ctx_factory, prob, theta=0.5, rtol=1e-13, x0=0, pc=1, norm=0, max_it=1000):
+    ctx = ctx_factory()
+    mass, stiff = prob["mass"], prob["stiff"]
+    n = mass.shape[0]
+    ctx.pde_set_matrices(n, 0, mass.indptr, mass.indices, mass.data, stiff.data)
+    ctx.pde_config(prob["C_m"], theta, rtol, 1e-50, max_it, pc, norm, x0)
+    return ctx
+
+
+@pytest.mark.parametrize("x0", [0, 1])
+def test_pde_single_step_tight(ctx_factory, x0):
+    prob = P.niederer_slab(0.5)
+    n = prob["mass"].shape[0]
+    rng = np.random.default_rng(3)
+    v_prev = -85.0 + 120.0 * rng.random(n)
+    ctx = _pde_ctx(ctx_factory, prob, x0=x0)
+    idx = np.nonzero(prob["stim_load"])[0]
+    ctx.stim_add(idx, prob["stim_load"][idx], 0.0, 2.0, prob["stim_amp"])
+    ctx.set_v_prev(v_prev)
+    ctx.pde_step(0.5, 0.55)
+    got = ctx.get_v(np.empty(n))
+    its, rnorm, reason = ctx.ksp_info()
+    ref = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [om_mono.Stimulus.window(prob["stim_load"], 0.0, 2.0, prob["stim_amp"])],
+                                  C_m=prob["C_m"], theta=0.5, solver="lu")
+    ref.v_[:] = v_prev
+    ref.step((0.5, 0.55))
+    err = np.abs(got - ref.state).max() / np.abs(ref.state).max()
+    assert reason > 0, (its, rnorm, reason)
+    assert err <= 1e-8, f"PDE step rel err {err:.3e} after {its} iterations"
+    assert err <= 1e-10  # what a tight solve actually delivers
+    ctx.close()
+
+
+def test_pde_matches_petsc_style_cg_iteration_count(ctx_factory):
+    """Same algorithm, same tolerance -> same iteration count and the same iterate as the oracle's KSPCG restatement."""
+    prob = P.niederer_slab(0.5)
+    n = prob["mass"].shape[0]
+    rng = np.random.default_rng(5)
+    v_prev = -85.0 + 120.0 * rng.random(n)
+    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-5)
+    ctx.set_v_prev(v_prev)
+    ctx.pde_step(0.0, 0.05)
+    got = ctx.get_v(np.empty(n))
+    its, rnorm, reason = ctx.ksp_info()
+    ref = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [], C_m=prob["C_m"], theta=0.5, solver="cg-jacobi", rtol=1e-5)
+    ref.v_[:] = v_prev
+    ref.step((0.0, 0.05))
+    assert its == ref.ksp["iterations"], (its, ref.ksp)
+    assert reason == ref.ksp["reason"]
+    assert abs(rnorm - ref.ksp["residual_norm"]) <= 1e-6 * ref.ksp["residual_norm"]
+    assert np.abs(got - ref.state).max() <= 1e-10 * np.abs(ref.state).max()
+    ctx.close()
+
+
+def test_pde_dt_change_rebuilds_matrices(ctx_factory):
+    prob = P.niederer_slab(1.0)
+    n = prob["mass"].shape[0]
+    rng = np.random.default_rng(11)
+    v0 = rng.random(n)
+    ctx = _pde_ctx(ctx_factory, prob)
+    ref = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [], C_m=prob["C_m"], theta=0.5, solver="lu")
+    ctx.set_v_prev(v0)
+    ref.v_[:] = v0
+    t = 0.0
+    for dt in (0.05, 0.05, 0.2, 0.01):
+        ctx.pde_step(t, t + dt)
+        ref.step((t, t + dt))
+        ctx.pde_assign_previous()
+        ref.assign_previous()
+        t += dt
+    got = ctx.get_v(np.empty(n))
+    assert np.abs(got - ref.state).max() <= 1e-9 * np.abs(ref.state).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("theta_split", [1.0, 0.5])
+def test_split_steps_niederer_small(ctx_factory, theta_split):
+    """A few fused split steps (TP06 GRL1 + CN diffusion + S1 stimulus) against the oracle's literal
+    restatement of MonodomainSplittingSolver.step."""
+    import beat_b200.models.tp06 as hm
+
+    prob = P.niederer_slab(0.5)
+    n = prob["mass"].shape[0]
+    om = P.oracle_model("tp06")
+    params = om.init_parameter_values(stim_amplitude=0.0)
+    y0 = om.init_state_values()
+    stim = om_mono.Stimulus.window(prob["stim_load"], 0.0, 2.0, prob["stim_amp"])
+    pde = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [stim], C_m=prob["C_m"], theta=0.5, solver="lu")
+    ode = om_mono.ODESolver(v_pde=pde.state, init_states=y0, parameters=params, fun=om.generalized_rush_larsen,
+                            num_states=len(y0), v_index=om.state_index("V"))
+    ref = om_mono.SplittingSolver(pde, ode, theta=theta_split)
+
+    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-12)
+    idx = np.nonzero(prob["stim_load"])[0]
+    ctx.stim_add(idx, prob["stim_load"][idx], 0.0, 2.0, prob["stim_amp"])
+    ctx.ode_create(1, 1, n, om.state_index("V"), len(y0))
+    ctx.ode_set_states(np.repeat(y0[:, None], n, axis=1))
+    ctx.ode_set_params(params, hm.generalized_rush_larsen.derived(params))
+    # MonodomainSplittingSolver.__post_init__ (monodomain_solver.py:33-37)
+    ctx.ode_to_dolfin()
+    ctx.ode_to_pde()
+    ctx.pde_assign_previous()
+
+    dt, nsteps = 0.05, 40
+    t = 0.0
+    for k in range(nsteps):
+        ref.step((t, t + dt))
+        ctx.split_step(t, t + dt, theta_split)
+        t += dt
+    got_v = ctx.get_v(np.empty(n))
+    got_states = ctx.ode_get_states()
+    assert np.abs(got_v - pde.state).max() <= 1e-8 * np.abs(pde.state).max()
+    scale = np.abs(ode.values).max(axis=1, keepdims=True)
+    assert (np.abs(got_states - ode.values) / scale).max() <= 1e-8
+    # post-condition of a split step: states[V] == v == v_
+    assert np.array_equal(got_states[om.state_index("V")], got_v)
+    assert np.array_equal(ctx.get_v_prev(np.empty(n)), got_v)
+    assert pde.state.max() > 0.0, "stimulated corner must have depolarised"
+    ctx.close()

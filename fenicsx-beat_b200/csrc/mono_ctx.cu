@@ -165,7 +165,7 @@ int mono_ctx_destroy(mono_ctx* c) {
     for (auto& ev : t)
       if (ev) cudaEventDestroy(ev);
   for (auto ev : c->ev_pool) cudaEventDestroy(ev);
-  extern int halo_destroy(mono_ctx*);
+
   halo_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;

@@ -143,3 +143,4 @@ int probes_launch(mono_ctx* c, double t0);
 
 // halo.cu
 int halo_refresh(mono_ctx* c, double* vec);  // owner -> ghost copy of an n_local vector (no-op for 1 rank)
+int halo_destroy(mono_ctx* c);

@@ -1,0 +1,692 @@
+"""Light host-side stand-ins for the slice of dolfinx / ufl that the monodomain step touches.
+
+In the reference, dolfinx builds the mesh, the P1 dof map, the partition and the constant matrices once
+at set-up (north_star: "host code stays Python").  dolfinx cannot be installed in this environment
+(SURVEY.md section 0), so this module provides the same *objects with the same attribute names* for the
+structured meshes the reference's tests, README and Niederer demo use:
+
+    create_unit_interval / create_unit_square / create_rectangle / create_box      (dolfinx.mesh.*)
+    locate_entities / locate_entities_boundary / meshtags                          (dolfinx.mesh.*)
+    functionspace / Function / Constant                                             (dolfinx.fem.*)
+    Measure, conditional/And/ge/le/..., SpatialCoordinate-free separable sources    (ufl.*)
+
+Partitioning follows dolfinx's IndexMap layout: owned dofs first, ghosts after, grouped by owner
+(tests/test_odesolver.py:63 of the reference reads size_local + num_ghosts).  A rank's local cells are
+all cells that touch an owned vertex, so owned matrix rows assemble completely without communication.
+
+Mesh splits restated from dolfinx (not verifiable here): unit square = "right" diagonal, box = six Kuhn
+tetrahedra per hexahedron sharing the (0,0,0)-(1,1,1) diagonal (src/beat/geometry.py:133-139).
+"""
+
+from __future__ import annotations
+
+import itertools
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Callable, Sequence
+
+import numpy as np
+
+
+# ----------------------------------------------------------------------------------------- comm
+@dataclass(frozen=True)
+class Comm:
+    """Rank / size carrier (stands in for mpi4py's communicator; collectives go through NCCL)."""
+
+    rank: int = 0
+    size: int = 1
+
+    def Get_rank(self) -> int:
+        return self.rank
+
+    def Get_size(self) -> int:
+        return self.size
+
+
+def comm_world() -> Comm:
+    return Comm(int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
+
+
+COMM_SELF = Comm(0, 1)
+
+
+# ------------------------------------------------------------------------------------- index map
+@dataclass
+class IndexMap:
+    size_local: int
+    ghosts: np.ndarray  # global ids of ghosts, grouped by owner
+    owners: np.ndarray  # owner rank of each ghost
+    local_to_global: np.ndarray  # owned then ghosts
+    size_global: int
+    # halo pattern (neighbour ranks ascending)
+    nbr_ranks: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    send_ptr: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int32))
+    send_idx: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    recv_ptr: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int32))
+
+    @property
+    def num_ghosts(self) -> int:
+        return int(self.ghosts.shape[0])
+
+
+class _Geometry:
+    def __init__(self, x: np.ndarray):
+        self.x = x  # (n_local, 3) like dolfinx (always 3 columns)
+
+
+class _Topology:
+    def __init__(self, dim: int, index_map: IndexMap):
+        self.dim = dim
+        self._vertex_map = index_map
+
+    def index_map(self, dim: int) -> IndexMap:
+        if dim != 0:
+            raise NotImplementedError("only the vertex index map is provided")
+        return self._vertex_map
+
+
+class Mesh:
+    """Simplicial P1 mesh, local part of one rank."""
+
+    def __init__(self, comm: Comm, points: np.ndarray, cells: np.ndarray, index_map: IndexMap, tdim: int,
+                 cell_global: np.ndarray | None = None, info: dict | None = None):
+        self.comm = comm
+        pts3 = np.zeros((points.shape[0], 3))
+        pts3[:, : points.shape[1]] = points
+        self.geometry = _Geometry(pts3)
+        self.gdim = points.shape[1]
+        self.cells = np.ascontiguousarray(cells, dtype=np.int64)  # local vertex ids, (ncell, tdim+1)
+        self.topology = _Topology(tdim, index_map)
+        self.index_map = index_map
+        self.cell_global = cell_global
+        self.info = info or {}
+        self._device_ctx = None
+        self._boundary_facets = None
+
+    # one device context per mesh (= per rank/GPU): PDE and ODE stages of a simulation share it
+    def device_context(self):
+        if self._device_ctx is None:
+            from ._lib import Context
+
+            dev = int(os.environ.get("LOCAL_RANK", "0")) if self.comm.size > 1 else int(os.environ.get("MONO_DEVICE", "0"))
+            self._device_ctx = Context(dev)
+        return self._device_ctx
+
+    def new_device_context(self):
+        """Drop the cached context (a new simulation on the same mesh needs a fresh one)."""
+        self._device_ctx = None
+        return self.device_context()
+
+    @property
+    def num_local_vertices(self) -> int:
+        return self.geometry.x.shape[0]
+
+    def boundary_facets(self) -> np.ndarray:
+        """Exterior facets of the GLOBAL mesh among the local cells, as sorted local vertex tuples."""
+        if self._boundary_facets is None:
+            d = self.topology.dim
+            fac = np.concatenate([np.delete(self.cells, a, axis=1) for a in range(d + 1)], axis=0)
+            fac = np.sort(fac, axis=1)
+            uniq, counts = np.unique(fac, axis=0, return_counts=True)
+            cand = uniq[counts == 1]
+            # a facet seen once locally may be interior to the global mesh (its other cell lives on another
+            # rank); such a facet has only ghost/boundary vertices.  Structured generators pass a predicate.
+            on_bnd = self.info.get("on_boundary")
+            if on_bnd is not None:
+                keep = np.ones(cand.shape[0], dtype=bool)
+                x = self.geometry.x
+                keep &= on_bnd(x[cand].transpose(2, 0, 1))
+                cand = cand[keep]
+            self._boundary_facets = cand
+        return self._boundary_facets
+
+
+def _partition_1d(n_planes: int, size: int) -> np.ndarray:
+    """Plane ranges [start[r], start[r+1]) of a balanced 1-D block partition."""
+    base, rem = divmod(n_planes, size)
+    counts = np.array([base + (1 if r < rem else 0) for r in range(size)])
+    return np.concatenate([[0], np.cumsum(counts)])
+
+
+def _build_local(comm: Comm, cells_g: np.ndarray, coords_of: Callable[[np.ndarray], np.ndarray], owner_of: Callable[[np.ndarray], np.ndarray],
+                 n_global: int, tdim: int, info: dict) -> Mesh:
+    """cells_g: global vertex ids of every cell touching a vertex owned by this rank."""
+    rank = comm.rank
+    gids = np.unique(cells_g)
+    own = owner_of(gids)
+    owned = gids[own == rank]
+    ghost_mask = own != rank
+    ghosts = gids[ghost_mask]
+    gown = own[ghost_mask]
+    order = np.lexsort((ghosts, gown))
+    ghosts, gown = ghosts[order], gown[order]
+    l2g = np.concatenate([owned, ghosts])
+    # global -> local through a sorted lookup
+    sorter = np.argsort(l2g)
+    cells_l = sorter[np.searchsorted(l2g, cells_g, sorter=sorter)]
+    n_owned = owned.shape[0]
+
+    # halo pattern, computed without communication (see module docstring)
+    nbr = np.unique(gown).astype(np.int32)
+    recv_ptr = np.concatenate([[0], np.cumsum([np.count_nonzero(gown == q) for q in nbr])]).astype(np.int32)
+    send_lists = []
+    if nbr.size:
+        cell_owner = own[np.searchsorted(gids, cells_g)]  # owner of each cell vertex
+        for q in nbr:
+            touches_q = (cell_owner == q).any(axis=1)
+            mine = cells_g[touches_q][cell_owner[touches_q] == rank]
+            send_g = np.unique(mine)
+            send_lists.append(sorter[np.searchsorted(l2g, send_g, sorter=sorter)].astype(np.int32))
+    send_ptr = np.concatenate([[0], np.cumsum([len(s) for s in send_lists])]).astype(np.int32)
+    send_idx = np.concatenate(send_lists).astype(np.int32) if send_lists else np.zeros(0, np.int32)
+    imap = IndexMap(n_owned, ghosts, gown.astype(np.int32), l2g, n_global, nbr, send_ptr, send_idx, recv_ptr)
+    return Mesh(comm, coords_of(l2g), cells_l, imap, tdim, info=info)
+
+
+def create_interval(comm: Comm, n: int, points=(0.0, 1.0)) -> Mesh:
+    a, b = points
+    starts = _partition_1d(n + 1, comm.size)
+    lo, hi = starts[comm.rank], starts[comm.rank + 1]
+    c0, c1 = max(lo - 1, 0), min(hi, n)
+    ids = np.arange(c0, c1)
+    cells = np.stack([ids, ids + 1], axis=1)
+    h = (b - a) / n
+    return _build_local(
+        comm, cells, lambda g: (a + h * g).reshape(-1, 1), lambda g: np.searchsorted(starts, g, side="right") - 1, n + 1, 1,
+        {"kind": "interval", "n": (n,), "p0": (a,), "p1": (b,),
+         "on_boundary": lambda x: np.all(np.isclose(x[0], a) | np.isclose(x[0], b), axis=1)},
+    )
+
+
+def create_unit_interval(comm: Comm, n: int) -> Mesh:
+    return create_interval(comm, n, (0.0, 1.0))
+
+
+def create_rectangle(comm: Comm, points, n, cell_type=None, dtype=np.float64) -> Mesh:
+    (x0, y0), (x1, y1) = (tuple(points[0])[:2], tuple(points[1])[:2])
+    nx, ny = int(n[0]), int(n[1])
+    starts = _partition_1d(nx + 1, comm.size)
+    lo, hi = starts[comm.rank], starts[comm.rank + 1]
+    c0, c1 = max(lo - 1, 0), min(hi, nx)
+    ix, iy = np.meshgrid(np.arange(c0, c1), np.arange(ny), indexing="xy")
+    v0 = (iy * (nx + 1) + ix).ravel()
+    v1, v2 = v0 + 1, v0 + (nx + 1)
+    v3 = v2 + 1
+    cells = np.concatenate([np.stack([v0, v1, v3], axis=1), np.stack([v0, v2, v3], axis=1)], axis=0)
+    hx, hy = (x1 - x0) / nx, (y1 - y0) / ny
+
+    def coords(g):
+        return np.stack([x0 + hx * (g % (nx + 1)), y0 + hy * (g // (nx + 1))], axis=1)
+
+    def on_boundary(x):  # x: (3, nfacets, nverts)
+        return (
+            np.all(np.isclose(x[0], x0), axis=1) | np.all(np.isclose(x[0], x1), axis=1)
+            | np.all(np.isclose(x[1], y0), axis=1) | np.all(np.isclose(x[1], y1), axis=1)
+        )
+
+    return _build_local(
+        comm, cells, coords, lambda g: np.searchsorted(starts, g % (nx + 1), side="right") - 1, (nx + 1) * (ny + 1), 2,
+        {"kind": "rectangle", "n": (nx, ny), "p0": (x0, y0), "p1": (x1, y1), "on_boundary": on_boundary},
+    )
+
+
+def create_unit_square(comm: Comm, nx: int, ny: int, cell_type=None) -> Mesh:
+    return create_rectangle(comm, [np.array([0.0, 0.0]), np.array([1.0, 1.0])], [nx, ny])
+
+
+def create_box(comm: Comm, points, n, cell_type=None, dtype=np.float64) -> Mesh:
+    p0 = tuple(float(v) for v in points[0])
+    p1 = tuple(float(v) for v in points[1])
+    nx, ny, nz = (int(v) for v in n)
+    starts = _partition_1d(nx + 1, comm.size)
+    lo, hi = starts[comm.rank], starts[comm.rank + 1]
+    c0, c1 = max(lo - 1, 0), min(hi, nx)
+    iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(c0, c1), indexing="ij")
+    v0 = ((iz * (ny + 1) + iy) * (nx + 1) + ix).ravel().astype(np.int64)
+    sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+    tets = []
+    for perm in itertools.permutations((sx, sy, sz)):
+        a = v0 + perm[0]
+        b = a + perm[1]
+        tets.append(np.stack([v0, a, b, b + perm[2]], axis=1))
+    cells = np.concatenate(tets, axis=0)
+    h = [(p1[k] - p0[k]) / m for k, m in enumerate((nx, ny, nz))]
+
+    def coords(g):
+        gx = g % (nx + 1)
+        gy = (g // (nx + 1)) % (ny + 1)
+        gz = g // sz
+        return np.stack([p0[0] + h[0] * gx, p0[1] + h[1] * gy, p0[2] + h[2] * gz], axis=1)
+
+    def on_boundary(x):
+        m = np.zeros(x.shape[1], dtype=bool)
+        for k in range(3):
+            m |= np.all(np.isclose(x[k], p0[k]), axis=1) | np.all(np.isclose(x[k], p1[k]), axis=1)
+        return m
+
+    return _build_local(
+        comm, cells, coords, lambda g: np.searchsorted(starts, g % (nx + 1), side="right") - 1,
+        (nx + 1) * (ny + 1) * (nz + 1), 3,
+        {"kind": "box", "n": (nx, ny, nz), "p0": p0, "p1": p1, "on_boundary": on_boundary},
+    )
+
+
+# ---------------------------------------------------------------------------- entities and tags
+@dataclass
+class MeshTags:
+    mesh: Mesh
+    dim: int
+    indices: np.ndarray  # cell ids (dim == tdim) or rows of `facets` (dim == tdim-1) or vertex ids (dim == 0)
+    values: np.ndarray
+    facets: np.ndarray | None = None  # (nfacets, tdim) local vertex ids, for facet tags
+
+    def find(self, value: int) -> np.ndarray:
+        return self.indices[self.values == value]
+
+
+def locate_entities(mesh: Mesh, dim: int, marker: Callable[[np.ndarray], np.ndarray]) -> np.ndarray:
+    """Entities whose vertices ALL satisfy ``marker(x)`` (x has shape (3, npoints)), dolfinx semantics."""
+    ok = np.asarray(marker(mesh.geometry.x.T), dtype=bool)
+    if dim == mesh.topology.dim:
+        return np.nonzero(ok[mesh.cells].all(axis=1))[0].astype(np.int32)
+    if dim == 0:
+        return np.nonzero(ok)[0].astype(np.int32)
+    raise NotImplementedError("interior sub-entities: use locate_entities_boundary for facets")
+
+
+class _FacetSelection(np.ndarray):
+    """int32 ids into mesh.boundary_facets() (keeps the facet table attached for meshtags)."""
+
+
+def locate_entities_boundary(mesh: Mesh, dim: int, marker: Callable[[np.ndarray], np.ndarray]) -> np.ndarray:
+    if dim != mesh.topology.dim - 1:
+        raise NotImplementedError("only boundary facets are provided")
+    fac = mesh.boundary_facets()
+    ok = np.asarray(marker(mesh.geometry.x.T), dtype=bool)
+    return np.nonzero(ok[fac].all(axis=1))[0].astype(np.int32)
+
+
+def meshtags(mesh: Mesh, dim: int, entities: np.ndarray, values) -> MeshTags:
+    entities = np.asarray(entities, dtype=np.int32)
+    values = np.broadcast_to(np.asarray(values, dtype=np.int32), entities.shape).copy()
+    facets = mesh.boundary_facets() if dim == mesh.topology.dim - 1 and dim != 0 else None
+    if dim == 0 and mesh.topology.dim == 1:
+        facets = mesh.boundary_facets()
+    return MeshTags(mesh, dim, entities, values, facets)
+
+
+class Measure:
+    """ufl.Measure("dx" | "ds", domain=mesh, subdomain_data=tags); calling it selects a marker."""
+
+    def __init__(self, kind: str, domain: Mesh | None = None, subdomain_data: MeshTags | None = None, marker: int | None = None,
+                 metadata: dict | None = None):
+        if kind not in ("dx", "ds"):
+            raise ValueError("measure must be 'dx' or 'ds'")
+        self.kind, self.domain, self.subdomain_data, self.marker = kind, domain, subdomain_data, marker
+        self.metadata = metadata
+
+    def __call__(self, marker: int | None = None, **kw) -> "Measure":
+        return Measure(self.kind, kw.get("domain", self.domain), self.subdomain_data, marker, self.metadata)
+
+
+def dx(domain: Mesh | None = None, **kw) -> Measure:
+    return Measure("dx", domain, **kw)
+
+
+# ------------------------------------------------------------------------ functions, constants
+class Constant:
+    """dolfinx.fem.Constant: a mutable scalar / small array with ``.value``."""
+
+    def __init__(self, mesh: Mesh | None, value):
+        self.mesh = mesh
+        self._value = np.array(value, dtype=np.float64)
+
+    @property
+    def value(self):
+        return self._value
+
+    @value.setter
+    def value(self, v):
+        self._value[...] = v
+
+    def __float__(self) -> float:
+        return float(self._value)
+
+
+class Vector:
+    """``Function.x``: host mirror of a device vector with explicit coherence.
+
+    ``.array`` returns the (writable) host array, downloading first if the device copy is newer; because
+    the caller may write into it, the next device operation re-uploads it.  ``.array_ro`` gives a
+    read-only view without that upload.
+    """
+
+    def __init__(self, n: int):
+        self._host = np.zeros(n, dtype=np.float64)
+        self._download: Callable[[np.ndarray], None] | None = None
+        self._upload: Callable[[np.ndarray], None] | None = None
+        self.device_newer = False
+        self.host_dirty = False
+
+    def bind(self, download, upload, push_now: bool = True):
+        self._download, self._upload = download, upload
+        self.host_dirty = push_now
+        self.device_newer = False
+
+    def _pull(self):
+        if self.device_newer and self._download is not None:
+            self._download(self._host)
+            self.device_newer = False
+
+    @property
+    def array(self) -> np.ndarray:
+        self._pull()
+        if self._upload is not None:
+            self.host_dirty = True
+        return self._host
+
+    @property
+    def array_ro(self) -> np.ndarray:
+        self._pull()
+        v = self._host.view()
+        v.flags.writeable = False
+        return v
+
+    def flush_to_device(self):
+        if self.host_dirty and self._upload is not None:
+            self._upload(self._host)
+        self.host_dirty = False
+
+    def mark_device_newer(self):
+        self.device_newer = True
+        self.host_dirty = False
+
+    def scatter_forward(self):
+        """Ghost refresh.  The device step already refreshes ghosts of the solution (halo_refresh)."""
+        return None
+
+
+class _Element:
+    def __init__(self, family: str, degree: int):
+        self.family_name, self._degree = family, degree
+
+    def degree(self) -> int:
+        return self._degree
+
+
+class _DofMap:
+    def __init__(self, index_map: IndexMap):
+        self.index_map = index_map
+        self.index_map_bs = 1
+
+
+class FunctionSpace:
+    def __init__(self, mesh: Mesh, family: str = "Lagrange", degree: int = 1):
+        if family not in ("P", "Lagrange", "CG") or degree != 1:
+            raise NotImplementedError(
+                "the device path implements P1 Lagrange spaces (identity ODE<->PDE projection, "
+                "src/beat/utils.py:52-54); other spaces are a 'next' row of SURVEY.md section 8f"
+            )
+        self.mesh = mesh
+        self.dofmap = _DofMap(mesh.index_map)
+        self._element = _Element("Lagrange", 1)
+
+    def ufl_element(self):
+        return self._element
+
+    def tabulate_dof_coordinates(self) -> np.ndarray:
+        return self.mesh.geometry.x
+
+    @property
+    def num_local_dofs(self) -> int:
+        return self.mesh.index_map.size_local + self.mesh.index_map.num_ghosts
+
+
+def functionspace(mesh: Mesh, element=("Lagrange", 1)) -> FunctionSpace:
+    family, degree = element[0], element[1]
+    return FunctionSpace(mesh, family, degree)
+
+
+class Function:
+    def __init__(self, V: FunctionSpace, name: str = "f"):
+        self.function_space = V
+        self.name = name
+        self.x = Vector(V.num_local_dofs)
+
+    def ufl_element(self):
+        return self.function_space.ufl_element()
+
+    def interpolate(self, f: Callable[[np.ndarray], np.ndarray]):
+        self.x.array[:] = f(self.function_space.tabulate_dof_coordinates().T)
+
+
+# ----------------------------------------------------------------------- source-term expressions
+class TimeWindow:
+    """conditional(And(ge(time, start), le(time, end)), amplitude, 0): the reference's stimulus
+    (src/beat/stimulation.py:270).  Evaluated ON THE DEVICE: the window test is part of the RHS kernel."""
+
+    def __init__(self, time: Constant, start: float, end: float, amplitude):
+        self.time, self.start, self.end = time, float(start), float(end)
+        self.amplitude = amplitude  # float or Constant; Stimulus.assign overwrites it
+
+    def amplitude_now(self) -> float:
+        return float(self.amplitude)
+
+
+class TimeFunction:
+    """I_s = h(t): amplitude evaluated on the host at the theta-point each step, applied on the device."""
+
+    def __init__(self, time: Constant, h: Callable[[float], float]):
+        self.time, self.h = time, h
+        self.amplitude = 1.0
+
+    def amplitude_now(self) -> float:
+        return float(self.amplitude) * float(self.h(float(self.time.value)))
+
+
+class Separable(TimeFunction):
+    """I_s(x, t) = g(x) * h(t) (the manufactured sources of tests/test_monodomain.py:13-36): g enters the
+    load vector by quadrature at set-up, h(t) is the per-step amplitude."""
+
+    def __init__(self, time: Constant, g: Callable[[np.ndarray], np.ndarray], h: Callable[[float], float], degree: int = 6):
+        super().__init__(time, h)
+        self.g, self.degree = g, degree
+
+
+class _Cmp:
+    def __init__(self, op: str, a, b):
+        self.op, self.a, self.b = op, a, b
+
+
+class _And:
+    def __init__(self, *terms):
+        self.terms = terms
+
+
+def ge(a, b):
+    return _Cmp("ge", a, b)
+
+
+def le(a, b):
+    return _Cmp("le", a, b)
+
+
+def And(*terms):
+    return _And(*terms)
+
+
+def conditional(cond, true_value, false_value):
+    """Recognises the reference's window pattern and returns a device-evaluated TimeWindow."""
+    if isinstance(cond, _And) and len(cond.terms) == 2 and float(false_value) == 0.0:
+        lo = [t for t in cond.terms if isinstance(t, _Cmp) and t.op == "ge" and isinstance(t.a, Constant)]
+        hi = [t for t in cond.terms if isinstance(t, _Cmp) and t.op == "le" and isinstance(t.a, Constant)]
+        if len(lo) == 1 and len(hi) == 1 and lo[0].a is hi[0].a:
+            return TimeWindow(lo[0].a, float(lo[0].b), float(hi[0].b), true_value)
+    raise NotImplementedError(
+        "only conditional(And(ge(time, a), le(time, b)), amplitude, 0) is recognised; use TimeFunction / "
+        "Separable for other time dependences"
+    )
+
+
+# -------------------------------------------------------------------------------- P1 assembly
+def _simplex_measure_and_gradients(x: np.ndarray):
+    """x: (ncell, d+1, d).  Closed-form volume and P1 gradients (ncell, d+1, d) per dimension."""
+    d = x.shape[2]
+    e = x[:, 1:, :] - x[:, :1, :]  # edge vectors from vertex 0, (ncell, d, d)
+    if d == 1:
+        det = e[:, 0, 0]
+        g = np.empty((x.shape[0], 2, 1))
+        g[:, 1, 0] = 1.0 / det
+        g[:, 0, 0] = -g[:, 1, 0]
+        return np.abs(det), g
+    if d == 2:
+        a, b = e[:, 0], e[:, 1]
+        det = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+        g = np.empty((x.shape[0], 3, 2))
+        g[:, 1, 0], g[:, 1, 1] = b[:, 1] / det, -b[:, 0] / det
+        g[:, 2, 0], g[:, 2, 1] = -a[:, 1] / det, a[:, 0] / det
+        g[:, 0] = -(g[:, 1] + g[:, 2])
+        return np.abs(det) / 2.0, g
+    a, b, c = e[:, 0], e[:, 1], e[:, 2]
+    bc, ca, ab = np.cross(b, c), np.cross(c, a), np.cross(a, b)
+    det = np.einsum("ij,ij->i", a, bc)
+    g = np.empty((x.shape[0], 4, 3))
+    g[:, 1], g[:, 2], g[:, 3] = bc / det[:, None], ca / det[:, None], ab / det[:, None]
+    g[:, 0] = -(g[:, 1] + g[:, 2] + g[:, 3])
+    return np.abs(det) / 6.0, g
+
+
+def assemble_p1_local(mesh: Mesh, M) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """CSR (indptr int64, indices int32, mass, stiff) of the OWNED rows over local columns.
+
+    M: scalar, (d,d) tensor, or per-cell (ncell,d,d) tensor.  Entries are accumulated by sorting the
+    (row, col) keys - no dense or scipy intermediate - and both matrices share the sparsity."""
+    d = mesh.topology.dim
+    cells = mesh.cells
+    n_owned = mesh.index_map.size_local
+    n_local = mesh.num_local_vertices
+    x = mesh.geometry.x[:, :d][cells]
+    vol, g = _simplex_measure_and_gradients(x)
+    Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
+    if Mv.ndim == 0:
+        Ke = float(Mv) * np.einsum("eai,ebi->eab", g, g)
+    elif Mv.ndim == 2:
+        Ke = np.einsum("eai,ij,ebj->eab", g, Mv, g)
+    else:
+        Ke = np.einsum("eai,eij,ebj->eab", g, Mv, g)
+    Ke *= vol[:, None, None]
+    ref = (1.0 + np.eye(d + 1)) / ((d + 1) * (d + 2))
+    Me = vol[:, None, None] * ref[None]
+    rows = np.broadcast_to(cells[:, :, None], Ke.shape).ravel()
+    cols = np.broadcast_to(cells[:, None, :], Ke.shape).ravel()
+    keep = rows < n_owned
+    rows, cols = rows[keep], cols[keep]
+    key = rows * n_local + cols
+    order = np.argsort(key, kind="stable")
+    key = key[order]
+    first = np.concatenate([[True], key[1:] != key[:-1]])
+    starts = np.nonzero(first)[0]
+    mass = np.add.reduceat(Me.ravel()[keep][order], starts)
+    stiff = np.add.reduceat(Ke.ravel()[keep][order], starts)
+    ukey = key[starts]
+    urow = ukey // n_local
+    indices = (ukey % n_local).astype(np.int32)
+    indptr = np.zeros(n_owned + 1, dtype=np.int64)
+    np.add.at(indptr, urow + 1, 1)
+    indptr = np.cumsum(indptr)
+    return indptr, indices, mass, stiff
+
+
+def _gauss_simplex(d: int, degree: int):
+    m = degree // 2 + d
+    xg, wg = np.polynomial.legendre.leggauss(m)
+    xg, wg = 0.5 * (xg + 1.0), 0.5 * wg
+    if d == 1:
+        return np.stack([1.0 - xg, xg], axis=1), wg
+    if d == 2:
+        u, v = np.meshgrid(xg, xg, indexing="ij")
+        wu, wv = np.meshgrid(wg, wg, indexing="ij")
+        l1, l2 = u.ravel(), (v * (1 - u)).ravel()
+        return np.stack([1 - l1 - l2, l1, l2], axis=1), (wu * wv * (1 - u)).ravel() * 2.0
+    u, v, w = np.meshgrid(xg, xg, xg, indexing="ij")
+    wu, wv, ww = np.meshgrid(wg, wg, wg, indexing="ij")
+    l1, l2, l3 = u.ravel(), (v * (1 - u)).ravel(), (w * (1 - u) * (1 - v)).ravel()
+    return np.stack([1 - l1 - l2 - l3, l1, l2, l3], axis=1), (wu * wv * ww * (1 - u) ** 2 * (1 - v)).ravel() * 6.0
+
+
+def load_vector(mesh: Mesh, measure: Measure | None, marker: int | None, g: Callable | None = None, degree: int = 6) -> np.ndarray:
+    """s_i = int g(x) phi_i dz(marker) for OWNED dofs i (g == None: g = 1).  Length size_local."""
+    d = mesh.topology.dim
+    n_owned = mesh.index_map.size_local
+    out = np.zeros(mesh.num_local_vertices)
+    kind = measure.kind if measure is not None else "dx"
+    tags = measure.subdomain_data if measure is not None else None
+    if marker is None and measure is not None:
+        marker = measure.marker
+    if kind == "dx":
+        if marker is None or tags is None:
+            ids = np.arange(mesh.cells.shape[0])
+        else:
+            if tags.dim != d:
+                raise ValueError("dx measure needs cell tags")
+            ids = tags.find(marker)
+        ents = mesh.cells[ids]
+    else:
+        if tags is None or marker is None:
+            ents = mesh.boundary_facets()
+        else:
+            ents = tags.facets[tags.find(marker)]
+    if ents.shape[0] == 0:
+        return out[:n_owned]
+    k = ents.shape[1]
+    x = mesh.geometry.x[:, : mesh.gdim][ents]
+    if k == 1:
+        meas = np.ones(ents.shape[0])
+    elif k == 2:
+        meas = np.linalg.norm(x[:, 1] - x[:, 0], axis=1)
+    elif k == 3:
+        a, b = x[:, 1] - x[:, 0], x[:, 2] - x[:, 0]
+        if a.shape[1] == 2:
+            meas = 0.5 * np.abs(a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0])
+        else:
+            meas = 0.5 * np.linalg.norm(np.cross(a, b), axis=1)
+    else:
+        meas, _ = _simplex_measure_and_gradients(x)
+    if g is None:
+        np.add.at(out, ents.ravel(), np.repeat(meas / k, k))
+    else:
+        bary, wq = _gauss_simplex(k - 1, degree) if k > 1 else (np.ones((1, 1)), np.ones(1))
+        x3 = mesh.geometry.x[ents]
+        for q in range(bary.shape[0]):
+            xq = np.einsum("a,eag->eg", bary[q], x3)
+            gq = np.asarray(g(xq.T), dtype=np.float64) * wq[q] * meas
+            for a in range(k):
+                np.add.at(out, ents[:, a], gq * bary[q, a])
+    return out[:n_owned]
+
+
+def point_probe(mesh: Mesh, point: Sequence[float]):
+    """(local vertex ids, barycentric weights) of the cell containing ``point`` (P1 evaluation, what
+    scifem.evaluate_function does in demos/niederer_benchmark.py:285); None if no local cell has it."""
+    d = mesh.topology.dim
+    p = np.asarray(point, dtype=np.float64)[:d]
+    X = mesh.geometry.x[:, :d]
+    cx = X[mesh.cells]  # (ncell, d+1, d)
+    lo, hi = cx.min(axis=1), cx.max(axis=1)
+    cand = np.nonzero(np.all((p >= lo - 1e-12) & (p <= hi + 1e-12), axis=1))[0]
+    best = None
+    for c in cand:
+        T = (cx[c, 1:] - cx[c, 0]).T
+        lam = np.linalg.solve(T, p - cx[c, 0])
+        w = np.concatenate([[1.0 - lam.sum()], lam])
+        if w.min() >= -1e-10 and (best is None or w.min() > best[1].min()):
+            best = (mesh.cells[c].astype(np.int32), w)
+    if best is None:
+        return None
+    nodes, w = best
+    keep = np.abs(w) > 1e-14
+    return nodes[keep], w[keep]
+
+
+_ = math

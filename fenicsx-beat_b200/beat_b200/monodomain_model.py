@@ -1,0 +1,259 @@
+"""MonodomainModel on the device: the reference's BaseModel + MonodomainModel
+(src/beat/base_model.py:48-297, src/beat/monodomain_model.py:17-98) with the same constructor, attributes
+and step/solve semantics, talking to libmono_b200 through ctypes.
+
+Discrete problem (derived from monodomain_model.py:83-96, a, L = ufl.system(G)):
+    A = C_m*Mass + dt*theta*K            b = (C_m*Mass - dt*(1-theta)*K) v_ + dt * sum_k I_k(t0+theta*dt) s_k
+Mass/K are assembled once on the host (fem.assemble_p1_local) and handed to the device as CSR; the
+re-assembly the reference does every step (_update_rhs) becomes one SpMV in the persistent PDE kernel.
+"""
+
+from __future__ import annotations
+
+import logging
+import math
+from enum import Enum, auto
+from typing import Any, NamedTuple, Sequence
+
+import numpy as np
+
+from . import fem
+from ._lib import Context
+from .stimulation import Stimulus
+from .telemetry import BaseMonitor, NullMonitor
+
+logger = logging.getLogger(__name__)
+
+PC = {"none": 0, "jacobi": 1}
+NORM = {"preconditioned": 0, "unpreconditioned": 1, "natural": 2, "default": 0}
+
+
+class Status(str, Enum):
+    OK = auto()
+    NOT_CONVERGING = auto()
+
+
+class Results(NamedTuple):
+    state: fem.Function
+    status: Status
+
+
+def _transform_I_s(I_s, dZ: fem.Measure) -> list[Stimulus]:  # base_model.py:33-45
+    if I_s is None:
+        return []
+    if isinstance(I_s, Stimulus):
+        return [I_s]
+    if isinstance(I_s, (fem.TimeWindow, fem.TimeFunction, fem.Constant, float, int)):
+        return [Stimulus(expr=I_s, dZ=dZ)]
+    return list(I_s)
+
+
+class DeviceKSP:
+    """What monitor.record_ksp() receives: the PETSc KSP getters the reference's monitor calls
+    (src/beat/telemetry.py:67-76), answered from the device CG's result block."""
+
+    def __init__(self, ctx: Context):
+        self._ctx = ctx
+
+    def _info(self):
+        return self._ctx.ksp_info()
+
+    def getIterationNumber(self) -> int:
+        return self._info()[0]
+
+    def getResidualNorm(self) -> float:
+        return self._info()[1]
+
+    def getConvergedReason(self) -> int:
+        return self._info()[2]
+
+
+class MonodomainModel:
+    r"""Solve  C_m dV/dt - div(M grad V) - I_stim = 0  with the theta-rule, on one B200 per rank.
+
+    Parameters as in the reference (monodomain_model.py:27-40, base_model.py:73-82).  ``M`` is a float, a
+    :class:`fem.Constant`, a (d,d) array or a per-cell (ncell,d,d) array.  Solver selection follows
+    ``params["petsc_options"]``: ksp_type "cg" -> device CG with ksp_rtol / ksp_atol / ksp_max_it /
+    ksp_norm_type; pc_type "jacobi" | "none" are native, "hypre"/"gamg"/... map to Jacobi (the system is
+    mass-dominated); ksp_type "preonly" (the reference's LU/MUMPS default) is
+    reproduced by iterating the same CG to rtol 1e-12.
+    """
+
+    def __init__(self, time: fem.Constant, mesh: fem.Mesh, M, I_s=None, params: dict | None = None, C_m: float = 1.0,
+                 dx: fem.Measure | None = None, monitor: BaseMonitor | None = None, **kwargs: Any) -> None:
+        if kwargs:
+            logger.warning("Unused keyword arguments: %s", ", ".join(f"{k}={v}" for k, v in kwargs.items()))
+        self._mesh = mesh
+        self.time = time
+        self.dx = dx or fem.Measure("dx", domain=mesh)
+        self.monitor = monitor or NullMonitor()
+        self._M = M
+        self.C_m = fem.Constant(mesh, C_m)
+        self.parameters = type(self).default_parameters()
+        if params is not None:
+            self.parameters.update(params)
+        self._I_s = _transform_I_s(I_s, dZ=self.dx)
+        self._setup_state_space()
+        self._timestep = fem.Constant(mesh, self.parameters["default_timestep"])
+        self._setup_device()
+
+    # ---- reference surface ---------------------------------------------------------------------
+    @staticmethod
+    def default_parameters(solver_type: str = "direct") -> dict[str, Any]:  # base_model.py:136-168
+        if solver_type == "iterative":
+            petsc_options = {"ksp_type": "cg", "pc_type": "hypre", "pc_hypre_type": "boomeramg"}
+        else:
+            petsc_options = {"ksp_type": "preonly", "pc_type": "lu", "pc_factor_mat_solver_type": "mumps"}
+        return {
+            "theta": 0.5,
+            "degree": 1,
+            "family": "Lagrange",
+            "default_timestep": 1.0,
+            "jit_options": {},
+            "form_compiler_options": {},
+            "petsc_options": petsc_options,
+            "log_timings": False,
+            "timing_log_frequency": 1,
+            "use_custom_preconditioner": True,
+            # device-only knob: start CG from v_ instead of zero (fewer iterations, same fixed point)
+            "initial_guess_previous": False,
+        }
+
+    def _setup_state_space(self) -> None:  # monodomain_model.py:42-53
+        self.V = fem.functionspace(self._mesh, (self.parameters["family"], self.parameters["degree"]))
+        self.v_ = fem.Function(self.V, name="v_")
+        self._state = fem.Function(self.V, name="v")
+
+    @property
+    def state(self) -> fem.Function:
+        return self._state
+
+    def _solver_settings(self):
+        opts = self.parameters["petsc_options"] or {}
+        ksp = str(opts.get("ksp_type", "preonly"))
+        pc = str(opts.get("pc_type", "lu"))
+        if ksp == "preonly":
+            rtol, atol, max_it, pc_id = 1e-12, 1e-50, 10000, PC["jacobi"]
+        elif ksp == "cg":
+            rtol = float(opts.get("ksp_rtol", 1e-5))  # PETSc defaults
+            atol = float(opts.get("ksp_atol", 1e-50))
+            max_it = int(opts.get("ksp_max_it", 10000))
+            pc_id = PC["none"] if pc == "none" else PC["jacobi"]
+        else:
+            raise NotImplementedError(f"ksp_type={ksp!r}: the device solver is CG (ksp_type 'cg' or 'preonly')")
+        norm = NORM[str(opts.get("ksp_norm_type", "default"))]
+        x0 = 1 if self.parameters.get("initial_guess_previous") or opts.get("ksp_initial_guess_nonzero") else 0
+        return rtol, atol, max_it, pc_id, norm, x0
+
+    def _setup_device(self) -> None:
+        mesh = self._mesh
+        self._ctx = ctx = mesh.device_context()
+        if getattr(ctx, "n_local", 0):
+            self._ctx = ctx = mesh.new_device_context()
+        imap = mesh.index_map
+        indptr, indices, mass, stiff = fem.assemble_p1_local(mesh, self._M)
+        ctx.pde_set_matrices(imap.size_local, imap.num_ghosts, indptr, indices, mass, stiff)
+        if mesh.comm.size > 1:
+            from .dist import init_comm
+
+            init_comm(ctx, mesh.comm)
+            ctx.set_halo(imap.nbr_ranks, imap.send_ptr, imap.send_idx, imap.recv_ptr)
+        rtol, atol, max_it, pc_id, norm, x0 = self._solver_settings()
+        ctx.pde_config(float(self.C_m), float(self.parameters["theta"]), rtol, atol, max_it, pc_id, norm, x0)
+        self._stim_ids: list[int] = []
+        self._stim_amp: list[float] = []
+        for s in self._I_s:
+            expr = s.expr
+            g = expr.g if isinstance(expr, fem.Separable) else None
+            deg = expr.degree if isinstance(expr, fem.Separable) else 0
+            meas = s.dZ if s.dZ is not None else self.dx
+            load = fem.load_vector(mesh, meas, s.marker, g, deg)
+            idx = np.nonzero(load)[0].astype(np.int32)
+            if isinstance(expr, fem.TimeWindow):
+                t0, t1, amp = expr.start, expr.end, expr.amplitude_now()
+            else:
+                t0, t1, amp = -math.inf, math.inf, 0.0
+            self._stim_ids.append(ctx.stim_add(idx, load[idx], t0, t1, amp))
+            self._stim_amp.append(amp)
+        # host mirrors of the two PDE vectors
+        self._state.x.bind(ctx.get_v, ctx.set_v, push_now=False)
+        self.v_.x.bind(ctx.get_v_prev, ctx.set_v_prev, push_now=False)
+        self._state._owner = self
+        self.ksp = DeviceKSP(ctx)
+
+    def _push_stimulus_amplitudes(self) -> None:
+        """Host-side part of the source term: current amplitudes (Constants the user re-assigns every
+        step as in demos/pace_train.py:216-219, Stimulus.assign, or h(t) of a TimeFunction)."""
+        for k, s in enumerate(self._I_s):
+            expr = s.expr
+            if isinstance(expr, (fem.TimeWindow, fem.TimeFunction)):
+                amp = expr.amplitude_now()
+            else:
+                amp = float(expr)
+            if amp != self._stim_amp[k]:
+                self._ctx.stim_set_amplitude(self._stim_ids[k], amp)
+                self._stim_amp[k] = amp
+
+    def _flush_host(self) -> None:
+        self._state.x.flush_to_device()
+        self.v_.x.flush_to_device()
+
+    def assign_previous(self) -> None:  # monodomain_model.py:59-60
+        self._flush_host()
+        self._ctx.pde_assign_previous()
+        self.v_.x.mark_device_newer()
+
+    def step(self, interval) -> None:  # base_model.py:208-245
+        t0, t1 = interval
+        dt = t1 - t0
+        theta = self.parameters["theta"]
+        t = t0 + theta * dt
+        with self.monitor.track_time("pde_total_step"):
+            with self.monitor.track_time("pde_set_time"):
+                self.time.value = t
+            if not abs(dt - float(self._timestep)) < 1.0e-12:
+                self._timestep.value = dt  # the device rebuilds A, B inside mono_pde_step (K3)
+            self._push_stimulus_amplitudes()
+            self._flush_host()
+            with self.monitor.track_time("pde_linear_solve"):
+                self._ctx.pde_step(t0, t1)
+            self._state.x.mark_device_newer()
+            self.monitor.record_ksp(self.ksp)
+        self.monitor.advance_step(t0, t1)
+
+    def solve(self, interval, dt: float | None = None) -> Results:  # base_model.py:250-297
+        T0, T = interval
+        if dt is None:
+            dt = T - T0
+        t0 = T0
+        t1 = T0 + dt
+        while True:
+            self.step((t0, t1))
+            if (t1 + dt) > (T + 1e-12):
+                break
+            self.assign_previous()
+            t0 = t1
+            t1 = t0 + dt
+        return Results(state=self.state, status=Status.OK)
+
+    # ---- device extras ---------------------------------------------
+    def add_probe(self, point: Sequence[float]) -> int | None:
+        """Register a P1 point evaluation on the device; returns the probe id (None if the point is not
+        in this rank's cells)."""
+        hit = fem.point_probe(self._mesh, point)
+        if hit is None:
+            return None
+        nodes, w = hit
+        if not hasattr(self, "_n_probes"):
+            self._n_probes = 0
+        self._n_probes += 1
+        return self._ctx.probe_add(nodes, w)
+
+    def track_activation(self, threshold: float = 0.0) -> None:
+        self._ctx.probe_activation(threshold)
+
+    def probe_values(self) -> np.ndarray:
+        return self._ctx.probe_values(getattr(self, "_n_probes", 0))
+
+    def activation_times(self) -> np.ndarray:
+        return self._ctx.probe_activation_times(getattr(self, "_n_probes", 0))

@@ -1,0 +1,166 @@
+"""The reference's own known-answer tests for this path, run through the drop-in API on the device
+(reference files cited per test).  pytest -m gpu."""
+import numpy as np
+import pytest
+
+import _problems as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _beat():
+    import beat_b200 as beat
+
+    return beat
+
+
+def test_dolfin_ode_solver_data_movement():
+    """tests/test_odesolver.py:52-117 of the reference (shapes, step result, to_dolfin / ode_to_pde /
+    pde_to_ode / from_dolfin semantics) with FitzHugh-Nagumo forward Euler as the cell model."""
+    beat = _beat()
+    fem = beat.fem
+    om = P.oracle_model("fhn")
+    mesh = fem.create_unit_square(fem.COMM_SELF, 5, 5)
+    time = fem.Constant(mesh, 0.0)
+    pde = beat.MonodomainModel(time=time, mesh=mesh, M=1.0)
+    v_pde = pde.state
+    v_ode = fem.Function(fem.functionspace(mesh, ("P", 1)))
+    imap = v_ode.function_space.dofmap.index_map
+    n_ode = imap.size_local + imap.num_ghosts
+    s0, v0 = 2.0, 1.0
+    params = beat.models.fhn.init_parameter_values()
+    ode = beat.odesolver.DolfinODESolver(v_ode=v_ode, v_pde=v_pde, init_states=np.array([s0, v0]), parameters=params,
+                                         fun=beat.models.fhn.forward_explicit_euler, num_states=2, v_index=1)
+    assert ode.full_values.shape == (2, n_ode) and ode.values.shape == (2, n_ode)
+    assert np.allclose(ode.values[0], s0) and np.allclose(ode.values[1], v0)
+    dt = 0.1
+    want = om.forward_explicit_euler(np.array([[s0], [v0]]), 0.0, dt, params)
+    ode.step(0.0, dt)
+    assert np.allclose(ode.values[0], want[0], rtol=1e-14) and np.allclose(ode.values[1], want[1], rtol=1e-14)
+    assert np.allclose(v_ode.x.array, 0.0)  # the dolfin function is not updated by step
+    ode.to_dolfin()
+    assert np.allclose(v_ode.x.array, want[1])
+    assert np.allclose(v_pde.x.array, 0.0)
+    ode.ode_to_pde()
+    assert np.allclose(v_pde.x.array, want[1])
+    v_pde.x.array[:] = 1.0
+    ode.pde_to_ode()
+    assert np.allclose(v_ode.x.array, 1.0)
+    ode.from_dolfin()
+    assert np.allclose(ode.values[1], 1.0)
+    assert np.allclose(ode.values[0], want[0])
+    states = ode.states_to_dolfin()
+    assert len(states) == 2 and np.allclose(states[1].x.array, 1.0) and np.allclose(states[0].x.array, want[0])
+
+
+def test_rejects_python_callables():
+    beat = _beat()
+    fem = beat.fem
+    mesh = fem.create_unit_interval(fem.COMM_SELF, 4)
+    pde = beat.MonodomainModel(time=fem.Constant(mesh, 0.0), mesh=mesh, M=1.0)
+    with pytest.raises(TypeError):
+        beat.odesolver.DolfinODESolver(v_ode=fem.Function(pde.V), v_pde=pde.state, init_states=np.zeros(2), parameters=np.zeros(2),
+                                       fun=lambda **kw: None, num_states=2)
+    with pytest.raises(RuntimeError):
+        beat.models.tp06.generalized_rush_larsen(states=None, t=0, parameters=None, dt=0.1)
+
+
+def test_single_stimulation():
+    """tests/test_stimulation.py:12-46 of the reference: M = 0 on the unit interval, exact integrals."""
+    beat = _beat()
+    fem = beat.fem
+    mesh = fem.create_unit_interval(fem.COMM_SELF, 10)
+    value, end, start, dt = 2.0, 1.0, 0.5, 0.01
+    time = fem.Constant(mesh, 0.0)
+    expr = fem.conditional(fem.And(fem.ge(time, start), fem.le(time, end)), value, 0.0)
+    I_s = beat.stimulation.Stimulus(dZ=fem.dx(domain=mesh), expr=expr)
+    pde = beat.MonodomainModel(time=time, mesh=mesh, M=fem.Constant(mesh, 0.0), I_s=I_s)
+    pde.step((0.0, 0.4))
+    assert np.allclose(pde.state.x.array, 0.0)
+    t0 = 0.9
+    pde.solve((0.4, t0), dt=dt)
+    assert np.allclose(pde.state.x.array, value * (t0 - start))
+    pde.solve((t0, end + dt), dt=dt)
+    assert np.allclose(pde.state.x.array, (end - start - dt) * value)
+    pde.solve((end + dt, 2 * end), dt=dt)
+    assert np.allclose(pde.state.x.array, (end - start - dt) * value)
+
+
+def test_double_stimulation():
+    """tests/test_stimulation.py:49-107 of the reference."""
+    beat = _beat()
+    fem = beat.fem
+    mesh = fem.create_unit_interval(fem.COMM_SELF, 10)
+    dt, value1, value2, start1, end1, start2, end2 = 0.01, 2.0, 3.0, 0.5, 1.0, 0.9, 1.5
+    time = fem.Constant(mesh, 0.0)
+    e1 = fem.conditional(fem.And(fem.ge(time, start1), fem.le(time, end1)), value1, 0.0)
+    e2 = fem.conditional(fem.And(fem.ge(time, start2), fem.le(time, end2)), value2, 0.0)
+    dx = fem.dx(domain=mesh)
+    pde = beat.MonodomainModel(time=time, mesh=mesh, M=fem.Constant(mesh, 0.0),
+                               I_s=[beat.stimulation.Stimulus(dZ=dx, expr=e1), beat.stimulation.Stimulus(dZ=dx, expr=e2)])
+    pde.step((0.0, 0.4))
+    assert np.allclose(pde.state.x.array, 0.0)
+    t0 = 0.9
+    pde.solve((0.4, t0), dt=dt)
+    assert np.allclose(pde.state.x.array, value1 * (t0 - start1))
+    pde.solve((t0, end1 + dt), dt=dt)
+    assert np.allclose(pde.state.x.array, (end1 - start1 - dt) * value1 + (end1 + dt - start2) * value2)
+    pde.solve((end1 + dt, end2 + dt), dt=dt)
+    want = (end1 - start1 - dt) * value1 + (end2 - start2 - dt) * value2
+    assert np.allclose(pde.state.x.array, want)
+    pde.solve((end2 + dt, 2 * end2), dt=dt)
+    assert np.allclose(pde.state.x.array, want)
+
+
+@pytest.mark.parametrize("M,err", [(0.0, 1e-4), (1.0, 2e-4), (2.0, 2e-4)])
+def test_monodomain_analytic(M, err):
+    """tests/test_monodomain.py:38-64 of the reference: PDE-only MMS, N=15, theta=0.5, dt=1e-3, 10 steps."""
+    from oracle import fem as ofem
+
+    beat = _beat()
+    fem = beat.fem
+    N, dt = 15, 0.001
+    T = 10 * dt
+    mesh = fem.create_unit_square(fem.COMM_SELF, N, N)
+    time = fem.Constant(mesh, 0.0)
+    g = lambda x: np.cos(2 * np.pi * x[0]) * np.cos(2 * np.pi * x[1])  # noqa: E731
+    h = lambda t: np.cos(t) + M * 8 * np.pi**2 * np.sin(t)  # noqa: E731
+    model = beat.MonodomainModel(time=time, mesh=mesh, M=M, I_s=fem.Separable(time, g, h, degree=8), params=dict(theta=0.5))
+    res = model.solve((0, T), dt=dt)
+    pts, cells = ofem.rectangle_mesh(N, N)
+    assert np.allclose(pts, mesh.geometry.x[:, :2])
+    e = ofem.l2_error(pts, cells, res.state.x.array, lambda x: g(x) * np.sin(T))
+    assert e < err
+
+
+def test_niederer_api_matches_oracle_and_probes():
+    """The packaged Niederer set-up (dx = 0.5) against the oracle's restatement, through the public API,
+    including the device-side probes / activation tracker."""
+    from beat_b200 import niederer
+    from oracle import monodomain as om_mono
+
+    solver, info = niederer.setup(dx=0.5, rtol=1e-12)
+    prob = P.niederer_slab(0.5)
+    om = P.oracle_model("tp06")
+    params = om.init_parameter_values(stim_amplitude=0.0)
+    y0 = om.init_state_values()
+    stim = om_mono.Stimulus.window(prob["stim_load"], 0.0, 2.0, prob["stim_amp"])
+    pde = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [stim], C_m=prob["C_m"], theta=0.5, solver="lu")
+    ode = om_mono.ODESolver(v_pde=pde.state, init_states=y0, parameters=params, fun=om.generalized_rush_larsen, num_states=19,
+                            v_index=om.state_index("V"))
+    ref = om_mono.SplittingSolver(pde, ode)
+    dt, t = 0.05, 0.0
+    act = {k: -1.0 for k in niederer.POINTS}
+    for _ in range(60):
+        solver.step((t, t + dt))
+        ref.step((t, t + dt))
+        if pde.state[0] > 0 and act["P1"] < 0:
+            act["P1"] = t
+        t += dt
+    v = solver.pde.state.x.array
+    assert np.abs(v - pde.state).max() <= 1e-8 * np.abs(pde.state).max()
+    assert np.abs(solver.ode.values - ode.values).max() <= 1e-7 * np.abs(ode.values).max()
+    got = solver.pde.activation_times()
+    assert got[info["probe_ids"]["P1"]] == pytest.approx(act["P1"], abs=1e-12)
+    assert act["P1"] > 0
+    assert np.allclose(solver.pde.probe_values()[info["probe_ids"]["P1"]], v[0])

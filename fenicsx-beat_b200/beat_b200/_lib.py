@@ -26,6 +26,8 @@ SIGNATURES = {
     "mono_last_error": (C.c_char_p, [C.c_void_p]),
     "mono_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "mono_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "mono_host_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "mono_host_free": (C.c_int, [C.c_void_p]),
     "mono_sync": (C.c_int, [C.c_void_p]),
     "mono_device_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), c_int64_p]),
     "mono_comm_unique_id": (C.c_int, [C.c_void_p]),
@@ -67,6 +69,8 @@ SIGNATURES = {
     "mono_timer_start": (C.c_int, [C.c_void_p, C.c_int]),
     "mono_timer_stop": (C.c_int, [C.c_void_p, C.c_int]),
     "mono_timer_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "mono_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "mono_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "mono_l2_flush": (C.c_int, [C.c_void_p]),
     "mono_stage_times_ms": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, C.c_int]),
     "mono_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
@@ -98,6 +102,40 @@ def load_library():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+class _PinnedBlock:
+    """Owner of one cudaMallocHost allocation; freed when the last NumPy view dies."""
+
+    def __init__(self, lib, ptr, nbytes):
+        self.lib, self.ptr, self.nbytes = lib, ptr, nbytes
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.lib.mono_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_zeros(shape, dtype=np.float64) -> np.ndarray:
+    """NumPy array in page-locked host memory (host mirrors of device vectors).  Falls back to pageable
+    memory when no CUDA device is usable (host-only unit tests of the set-up code): this only changes
+    the transfer rate, never where the computation runs."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    try:
+        lib = load_library()
+        ptr = C.c_void_p()
+        if lib.mono_host_alloc(nbytes, C.byref(ptr)) != 0 or not ptr:
+            raise MonoError("no pinned memory")
+    except (MonoError, OSError):
+        return np.zeros(shape, dtype=dtype)
+    block = _PinnedBlock(lib, ptr, nbytes)
+    buf = (C.c_char * max(nbytes, 8)).from_address(ptr.value)
+    buf._block = block  # keeps the allocation alive as long as any view of buf exists
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr[...] = 0
+    return arr
 
 
 def _dp(a: np.ndarray):
@@ -331,6 +369,14 @@ class Context:
     def timer_elapsed_ms(self, slot: int = 0) -> float:
         ms = C.c_float()
         self._ck(self.lib.mono_timer_elapsed_ms(self.h, slot, C.byref(ms)))
+        return ms.value
+
+    def event_record(self, idx: int):
+        self._ck(self.lib.mono_event_record(self.h, idx))
+
+    def event_elapsed_ms(self, idx0: int, idx1: int) -> float:
+        ms = C.c_float()
+        self._ck(self.lib.mono_event_elapsed_ms(self.h, idx0, idx1, C.byref(ms)))
         return ms.value
 
     def l2_flush(self):

@@ -25,6 +25,14 @@ class DeviceODE:
     derived: Callable[[np.ndarray], np.ndarray] = field(repr=False, compare=False)
     op_counts: dict = field(default_factory=dict, repr=False, compare=False)
 
+    # fp64-pipe instructions per operation of the generated code (csrc/ode_math.cuh "fast" binding):
+    # divide = reciprocal seed + 4 FMA + mul + 2 FMA; exp/log = libdevice polynomial kernels.
+    FP64_WEIGHTS = {"add": 1, "mul": 1, "div": 7, "exp": 17, "log": 25, "sqrt": 12, "pow": 60, "floor": 1, "cmp": 1}
+
+    def fp64_instr_per_node(self) -> float:
+        """Estimated fp64-pipe instructions one node-step issues (roofline numerator of K1)."""
+        return float(sum(self.FP64_WEIGHTS.get(k, 0) * v for k, v in self.op_counts.items()))
+
     def __call__(self, *args, **kwargs):
         raise RuntimeError(
             f"{self.model_tag}.{self.scheme} is a device kernel handle and cannot be evaluated on the CPU "

@@ -363,7 +363,9 @@ class Vector:
     """
 
     def __init__(self, n: int):
-        self._host = np.zeros(n, dtype=np.float64)
+        from ._lib import pinned_zeros
+
+        self._host = pinned_zeros(n)
         self._download: Callable[[np.ndarray], None] | None = None
         self._upload: Callable[[np.ndarray], None] | None = None
         self.device_newer = False

@@ -153,6 +153,7 @@ class MonodomainModel:
         imap = mesh.index_map
         indptr, indices, mass, stiff = fem.assemble_p1_local(mesh, self._M)
         ctx.pde_set_matrices(imap.size_local, imap.num_ghosts, indptr, indices, mass, stiff)
+        self._nnz_per_row = len(indices) / max(imap.size_local, 1)
         if mesh.comm.size > 1:
             from .dist import init_comm
 

@@ -165,10 +165,25 @@ int mono_ctx_destroy(mono_ctx* c) {
     for (auto& ev : t)
       if (ev) cudaEventDestroy(ev);
   for (auto ev : c->ev_pool) cudaEventDestroy(ev);
+  for (auto ev : c->marks)
+    if (ev) cudaEventDestroy(ev);
 
   halo_destroy(c);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+  return MONO_OK;
+}
+
+int mono_host_alloc(int64_t nbytes, void** out) {
+  if (!out || nbytes < 0) return mono_fail(nullptr, MONO_E_INVALID, "bad arguments");
+  *out = nullptr;
+  cudaError_t e = cudaMallocHost(out, (size_t)std::max<int64_t>(nbytes, 8));
+  if (e != cudaSuccess) return mono_fail(nullptr, MONO_E_CUDA, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  return MONO_OK;
+}
+
+int mono_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
   return MONO_OK;
 }
 
@@ -602,6 +617,23 @@ int mono_timer_elapsed_ms(mono_ctx* c, int slot, float* ms) {
   MONO_CHECK(c, slot >= 0 && slot < 8 && c->timers[slot][1], "timer not started");
   MONO_CUDA(c, cudaEventSynchronize(c->timers[slot][1]));
   MONO_CUDA(c, cudaEventElapsedTime(ms, c->timers[slot][0], c->timers[slot][1]));
+  return MONO_OK;
+}
+
+int mono_event_record(mono_ctx* c, int idx) {
+  MONO_CHECK(c, idx >= 0 && idx < (1 << 24), "event index out of range");
+  if ((size_t)idx >= c->marks.size()) c->marks.resize((size_t)idx + 1, nullptr);
+  if (!c->marks[idx]) MONO_CUDA(c, cudaEventCreate(&c->marks[idx]));
+  MONO_CUDA(c, cudaEventRecord(c->marks[idx], c->stream));
+  return MONO_OK;
+}
+
+int mono_event_elapsed_ms(mono_ctx* c, int idx0, int idx1, float* ms) {
+  MONO_CHECK(c, idx0 >= 0 && idx1 >= 0 && (size_t)idx0 < c->marks.size() && (size_t)idx1 < c->marks.size() &&
+                    c->marks[idx0] && c->marks[idx1],
+             "event mark not recorded");
+  MONO_CUDA(c, cudaEventSynchronize(c->marks[idx1]));
+  MONO_CUDA(c, cudaEventElapsedTime(ms, c->marks[idx0], c->marks[idx1]));
   return MONO_OK;
 }
 

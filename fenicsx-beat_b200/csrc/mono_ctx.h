@@ -104,6 +104,7 @@ struct mono_ctx {
 
   // ---- measurement ---------------------------------------------------------------------------
   cudaEvent_t timers[8][2] = {};
+  std::vector<cudaEvent_t> marks;    // mono_event_record pool
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   bool stage_timing = false;

@@ -73,6 +73,11 @@ int mono_sync(mono_ctx *ctx);
 /* write *n_sm, *cc_major, *cc_minor, *mem_bytes of the context's device */
 int mono_device_info(mono_ctx *ctx, int *n_sm, int *cc_major, int *cc_minor, int64_t *mem_bytes);
 
+/* Page-locked host memory for the host mirrors of device vectors (pde.state.x.array & co): transfers
+ * from/to it run at full PCIe rate.  Needs a CUDA device (MONO_E_CUDA otherwise). */
+int mono_host_alloc(int64_t nbytes, void **out);
+int mono_host_free(void *ptr);
+
 /* ---- multi-GPU (one rank per GPU; replaces the MPI communicator inside PETSc/dolfinx,
  *      base_model.py:203-206,236,242).  id is the 128-byte NCCL unique id made by rank 0 and
  *      distributed by the caller (bench.py uses torch.distributed).                               */
@@ -167,6 +172,11 @@ int mono_probe_activation_times(mono_ctx *ctx, double *times);
 int mono_timer_start(mono_ctx *ctx, int slot);
 int mono_timer_stop(mono_ctx *ctx, int slot);
 int mono_timer_elapsed_ms(mono_ctx *ctx, int slot, float *ms);
+/* numbered CUDA-event marks on the context's stream (the pool grows on demand; bench.py brackets every
+ * timed step with a pair so the L2 flush between steps stays outside the measurement).
+ * mono_event_elapsed_ms synchronises on mark idx1. */
+int mono_event_record(mono_ctx *ctx, int idx);
+int mono_event_elapsed_ms(mono_ctx *ctx, int idx0, int idx1, float *ms);
 /* overwrite a scratch buffer larger than L2 (evicts the working set between timed steps) */
 int mono_l2_flush(mono_ctx *ctx);
 /* per-stage device time accumulated since the last reset, in ms: [0]=ode [1]=pde(rhs+cg+halo) */

@@ -189,7 +189,7 @@ def run_b200(args):
     K, W = args.steps, args.warmup
 
     t_setup = time.perf_counter()
-    solver, info = nied.setup(dx=dx, comm=comm, L=(20.0 * world, 7.0, 3.0), probes=False)
+    solver, info = nied.setup(dx=dx, comm=comm, L=(20.0 * world, 7.0, 3.0), probes=False, ksp_type=args.ksp)
     ctx = solver.pde._ctx
     n_global, n_owned = info["n_global"], info["n_owned"]
     setup_s = time.perf_counter() - t_setup
@@ -305,7 +305,7 @@ def run_b200(args):
     ns = info["num_states"]
     ode_bytes = n_owned * (2.0 * 8.0 * ns + 8.0)
     ode_flop = n_owned * nied.tp06.generalized_rush_larsen.fp64_instr_per_node() * 2.0
-    roof_pde = {"kernel": "pde_step_kernel (RHS SpMV + stimulus + Jacobi-PCG, one persistent launch)", "bound": "hbm",
+    roof_pde = {"kernel": f"pde_{args.ksp}_kernel (RHS SpMV + stimulus + Jacobi-PCG, one persistent launch)", "bound": "hbm",
                 "achieved": pde_bytes / (pde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": pde_bytes / (pde_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "ms_per_launch": pde_ms, "algorithmic_bytes_per_launch": pde_bytes}
@@ -322,7 +322,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: Niederer slab {20 * world}x7x3 mm, dx={dx} mm, {n_global} nodes "
                                f"({n_owned} owned by rank 0), TP06 GRL1, Godunov split + CN diffusion "
-                               f"(Jacobi-PCG rtol 1e-5, x0=0), dt={dt} ms", "nodes": n_global,
+                               f"(Jacobi-preconditioned {args.ksp}, rtol 1e-5, x0=0), dt={dt} ms", "nodes": n_global,
                    "l2": "flushed (256 MiB memset) between timed steps; flush outside the CUDA events",
                    "parallelism": f"x-slab partition, {world} rank(s), one per GPU"},
         "warm_l2": {"value": n_global * K / (ms_warm * 1e-3), "ms_per_step": ms_warm / K,
@@ -356,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="niederer_dx0.2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ksp", default="cg", choices=["cg", "pipecg"], help="Krylov driver of the diffusion solve")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -48,6 +48,7 @@ SIGNATURES = {
     "mono_set_v_ode": (C.c_int, [C.c_void_p, c_double_p]),
     "mono_pde_set_matrices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_int64_p, c_int32_p, c_double_p, c_double_p]),
     "mono_pde_config": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mono_pde_set_ksp_type": (C.c_int, [C.c_void_p, C.c_int]),
     "mono_pde_set_dt": (C.c_int, [C.c_void_p, C.c_double]),
     "mono_stim_add": (C.c_int, [C.c_void_p, C.c_int64, c_int32_p, c_double_p, C.c_double, C.c_double, C.c_double]),
     "mono_stim_set_amplitude": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
@@ -75,6 +76,8 @@ SIGNATURES = {
     "mono_stage_times_ms": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, C.c_int]),
     "mono_stage_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "mono_bench_dfma": (C.c_int, [C.c_void_p, c_double_p]),
+    "mono_bench_grid_sync": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
+    "mono_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "mono_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
 }
 
@@ -289,6 +292,9 @@ class Context:
     def pde_config(self, C_m, theta, rtol, atol, max_it, pc_type, norm_type, x0_mode):
         self._ck(self.lib.mono_pde_config(self.h, C_m, theta, rtol, atol, max_it, pc_type, norm_type, x0_mode))
 
+    def pde_set_ksp_type(self, ksp_type: int):
+        self._ck(self.lib.mono_pde_set_ksp_type(self.h, ksp_type))
+
     def pde_set_dt(self, dt: float):
         self._ck(self.lib.mono_pde_set_dt(self.h, dt))
 
@@ -395,6 +401,17 @@ class Context:
         tf = C.c_double()
         self._ck(self.lib.mono_bench_dfma(self.h, C.byref(tf)))
         return tf.value
+
+    def bench_grid_sync(self, n: int = 1000) -> float:
+        us = C.c_float()
+        self._ck(self.lib.mono_bench_grid_sync(self.h, n, C.byref(us)))
+        return us.value
+
+    def debug_timeline(self, enable: bool = True, read: bool = True):
+        buf = (C.c_uint64 * 64)()
+        self._ck(self.lib.mono_debug_timeline(self.h, 1 if enable else 0, buf if read else None))
+        n = int(buf[0])
+        return [int(buf[1 + k]) for k in range(min(n, 63))]
 
     def launch_count(self) -> int:
         n = C.c_int64()

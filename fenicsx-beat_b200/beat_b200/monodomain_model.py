@@ -134,15 +134,16 @@ class MonodomainModel:
         pc = str(opts.get("pc_type", "lu"))
         if ksp == "preonly":
             rtol, atol, max_it, pc_id = 1e-12, 1e-50, 10000, PC["jacobi"]
-        elif ksp == "cg":
+        elif ksp in ("cg", "pipecg"):
             rtol = float(opts.get("ksp_rtol", 1e-5))  # PETSc defaults
             atol = float(opts.get("ksp_atol", 1e-50))
             max_it = int(opts.get("ksp_max_it", 10000))
             pc_id = PC["none"] if pc == "none" else PC["jacobi"]
         else:
-            raise NotImplementedError(f"ksp_type={ksp!r}: the device solver is CG (ksp_type 'cg' or 'preonly')")
+            raise NotImplementedError(f"ksp_type={ksp!r}: the device solvers are 'cg', 'pipecg' (and 'preonly' = tight cg)")
         norm = NORM[str(opts.get("ksp_norm_type", "default"))]
         x0 = 1 if self.parameters.get("initial_guess_previous") or opts.get("ksp_initial_guess_nonzero") else 0
+        self._ksp_type = 1 if ksp == "pipecg" else 0  # MONO_KSP_PIPECG / MONO_KSP_CG
         return rtol, atol, max_it, pc_id, norm, x0
 
     def _setup_device(self) -> None:
@@ -161,6 +162,7 @@ class MonodomainModel:
             ctx.set_halo(imap.nbr_ranks, imap.send_ptr, imap.send_idx, imap.recv_ptr)
         rtol, atol, max_it, pc_id, norm, x0 = self._solver_settings()
         ctx.pde_config(float(self.C_m), float(self.parameters["theta"]), rtol, atol, max_it, pc_id, norm, x0)
+        ctx.pde_set_ksp_type(self._ksp_type)
         self._stim_ids: list[int] = []
         self._stim_amp: list[float] = []
         for s in self._I_s:

@@ -138,8 +138,6 @@ int mono_ctx_create(int device, mono_ctx** out) {
   if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
   c->n_sm = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
-  if ((e = cudaMalloc(&c->bar, 2 * sizeof(unsigned))) != cudaSuccess) return bail("cudaMalloc", e);
-  cudaMemset(c->bar, 0, 2 * sizeof(unsigned));
   if ((e = cudaMalloc(&c->ksp_dev, sizeof(KspResult))) != cudaSuccess) return bail("cudaMalloc", e);
   cudaMemset(c->ksp_dev, 0, sizeof(KspResult));
   if ((e = cudaMallocHost(&c->ksp_host, sizeof(KspResult))) != cudaSuccess) return bail("cudaMallocHost", e);
@@ -154,8 +152,10 @@ int mono_ctx_destroy(mono_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (void* p : {(void*)c->states, (void*)c->v_ode, (void*)c->params_dev, (void*)c->slice_ptr, (void*)c->cols,
                   (void*)c->mass, (void*)c->stiff, (void*)c->A, (void*)c->B, (void*)c->dinv, (void*)c->x,
-                  (void*)c->v_prev, (void*)c->b, (void*)c->r, (void*)c->z, (void*)c->p0, (void*)c->p1, (void*)c->q,
-                  (void*)c->stims_dev, (void*)c->bar, (void*)c->partials, (void*)c->ksp_dev, (void*)c->probes_dev,
+                  (void*)c->v_prev, (void*)c->work[0], (void*)c->work[1], (void*)c->work[2], (void*)c->work[3],
+                  (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->t0, (void*)c->t1, (void*)c->stim_vec,
+                  (void*)c->recs, (void*)c->timeline_dev,
+                  (void*)c->ksp_dev, (void*)c->probes_dev,
                   (void*)c->probe_vals_dev, (void*)c->probe_act_dev, (void*)c->flush_buf, (void*)c->send_idx_dev,
                   (void*)c->send_buf, (void*)c->red_buf})
     if (p) cudaFree(p);
@@ -356,7 +356,7 @@ int mono_pde_set_matrices(mono_ctx* c, int64_t n_owned, int64_t n_ghost, const i
   int rc = pde_build_sell(c, indptr, indices, mass, stiff);
   if (rc) return rc;
   const int64_t nl = std::max<int64_t>(c->n_local, 32);
-  for (double** p : {&c->x, &c->v_prev, &c->b, &c->r, &c->z, &c->p0, &c->p1, &c->q, &c->dinv}) {
+  for (double** p : {&c->x, &c->v_prev, &c->dinv}) {
     MONO_CUDA(c, cudaMalloc(p, sizeof(double) * nl));
     MONO_CUDA(c, cudaMemsetAsync(*p, 0, sizeof(double) * nl, c->stream));
   }
@@ -381,6 +381,12 @@ int mono_pde_config(mono_ctx* c, double C_m, double theta, double rtol, double a
   c->norm_type = norm_type;
   c->x0_mode = x0_mode;
   c->have_dt = false;  // matrices depend on C_m / theta / pc
+  return MONO_OK;
+}
+
+int mono_pde_set_ksp_type(mono_ctx* c, int ksp_type) {
+  MONO_CHECK(c, ksp_type == MONO_KSP_CG || ksp_type == MONO_KSP_PIPECG, "unknown ksp_type");
+  c->ksp_type = ksp_type;
   return MONO_OK;
 }
 
@@ -413,7 +419,6 @@ int mono_stim_add(mono_ctx* c, int64_t nnz, const int32_t* idx, const double* va
     s.val = dv;
   }
   c->stims_host.push_back(s);
-  c->stims_dirty = true;
   return (int)c->stims_host.size() - 1;
 }
 
@@ -421,8 +426,7 @@ int mono_stim_set_amplitude(mono_ctx* c, int id, double amplitude) {
   MONO_CHECK(c, id >= 0 && id < (int)c->stims_host.size(), "bad stimulus id");
   if (c->stims_host[id].amp != amplitude) {
     c->stims_host[id].amp = amplitude;
-    c->stims_dirty = true;
-  }
+    }
   return MONO_OK;
 }
 
@@ -430,7 +434,6 @@ int mono_stim_set_window(mono_ctx* c, int id, double t_start, double t_end) {
   MONO_CHECK(c, id >= 0 && id < (int)c->stims_host.size(), "bad stimulus id");
   c->stims_host[id].t_start = t_start;
   c->stims_host[id].t_end = t_end;
-  c->stims_dirty = true;
   return MONO_OK;
 }
 
@@ -492,6 +495,7 @@ int mono_ksp_info(mono_ctx* c, int* iterations, double* residual_norm, int* reas
   if (iterations) *iterations = c->ksp_host->iterations;
   if (residual_norm) *residual_norm = c->ksp_host->rnorm;
   if (reason) *reason = c->ksp_host->reason;
+  if (c->ksp_host->error) return mono_fail(c, MONO_E_CUDA, "PDE kernel: grid synchronisation timed out");
   return MONO_OK;
 }
 
@@ -689,6 +693,28 @@ int mono_bench_dfma(mono_ctx* c, double* tflops) {
   cudaFree(out);
   if (tflops) *tflops = best;
   return MONO_OK;
+}
+
+int mono_debug_timeline(mono_ctx* c, int enable, uint64_t* stamps64) {
+  if (enable && !c->timeline_dev) {
+    MONO_CUDA(c, cudaMalloc(&c->timeline_dev, sizeof(unsigned long long) * 64));
+    MONO_CUDA(c, cudaMemsetAsync(c->timeline_dev, 0, sizeof(unsigned long long) * 64, c->stream));
+  }
+  if (stamps64 && c->timeline_dev) {
+    MONO_CUDA(c, cudaMemcpyAsync(stamps64, c->timeline_dev, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost, c->stream));
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  if (!enable && c->timeline_dev) {
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->timeline_dev);
+    c->timeline_dev = nullptr;
+  }
+  return MONO_OK;
+}
+
+int mono_bench_grid_sync(mono_ctx* c, int n, float* us_per_sync) {
+  MONO_CHECK(c, n > 0, "n must be positive");
+  return pde_bench_sync(c, n, us_per_sync);
 }
 
 int mono_launch_count(mono_ctx* c, int64_t* launches) {

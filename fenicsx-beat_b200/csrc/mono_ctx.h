@@ -4,6 +4,7 @@
 
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mono_abi.h"
@@ -26,6 +27,12 @@ struct KspResult {
   long long total_iterations;
   long long solves;
   int error;  // non-zero: kernel-side failure (e.g. barrier timeout)
+};
+
+// one record of the in-kernel grid synchronisation / reduction (pde_kernels.cu grid_allreduce)
+struct alignas(16) SyncRec {
+  double val;
+  unsigned long long gen;
 };
 
 struct ProbeDev {
@@ -70,22 +77,27 @@ struct mono_ctx {
   int32_t* cols = nullptr;               // sell_nnz
   double *mass = nullptr, *stiff = nullptr, *A = nullptr, *B = nullptr;  // sell_nnz each
   double* dinv = nullptr;                // 1/diag(A) (or 1 for PC none), n_owned
-  double *x = nullptr, *v_prev = nullptr, *b = nullptr, *r = nullptr, *z = nullptr, *p0 = nullptr,
-         *p1 = nullptr, *q = nullptr;  // vectors of n_local (x, v_prev, z, p*) or n_owned
+  double *x = nullptr, *v_prev = nullptr;  // solution and previous solution, n_local each
+  double* work[8] = {};                    // thread-private CG vectors in global memory (streaming mode only, lazy)
+  SyncRec *t0 = nullptr, *t1 = nullptr;    // the exchanged CG vector, tagged {value, generation}, n_local each
+  int ksp_type = MONO_KSP_CG;
   double C_m = 1.0, theta = 0.5, rtol = 1e-5, atol = 1e-50;
   int max_it = 10000, pc_type = MONO_PC_JACOBI, norm_type = MONO_NORM_PRECONDITIONED, x0_mode = MONO_X0_ZERO;
   double cur_dt = -1.0;
   bool have_dt = false;
   std::vector<StimDev> stims_host;
   std::vector<void*> stim_allocs;
-  StimDev* stims_dev = nullptr;
-  int stims_dev_cap = 0;
-  bool stims_dirty = true;
+  double* stim_vec = nullptr;                    // dense sum_k a_k(t) s_k of the currently active stimuli
+  std::vector<std::pair<int, double>> stim_sig;  // (stimulus id, amplitude) pairs stim_vec was built from
 
-  // grid-barrier + reduction scratch for the persistent PDE kernel
-  unsigned* bar = nullptr;      // [0]=count [1]=generation
-  double* partials = nullptr;   // 2 parities x 4 scalars x max_blocks
-  int pde_blocks = 0, pde_threads = 0;
+  // grid synchronisation records of the persistent PDE kernel: 2 parities x 4 scalars x blocks
+  SyncRec* recs = nullptr;
+  unsigned long long sync_gen = 1;  // next unused generation number (monotonic over the context's life)
+  int pde_blocks = 0, pde_workers = 0, pde_threads = 0, rows_per_thread = 1, max_width = 0;
+  unsigned long long* timeline_dev = nullptr;  // measurement: phase time stamps of the last PDE kernel (64 slots)
+  bool matsmem = false;             // ... and so do the A entries (one row per thread)
+  bool resident = false;            // the CG vectors of a CTA's rows fit in shared memory
+  size_t resident_smem = 0;
   KspResult* ksp_dev = nullptr;
   KspResult* ksp_host = nullptr;  // pinned
 
@@ -141,6 +153,7 @@ int pde_update_matrices(mono_ctx* c, double dt);
 int pde_launch_step(mono_ctx* c, double t_eval, double dt);
 int pde_setup_launch_config(mono_ctx* c);
 int probes_launch(mono_ctx* c, double t0);
+int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync);
 
 // halo.cu
 int halo_refresh(mono_ctx* c, double* vec);  // owner -> ghost copy of an n_local vector (no-op for 1 rank)

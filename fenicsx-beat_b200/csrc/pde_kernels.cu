@@ -9,19 +9,35 @@
 // Storage: SELL-32 (sliced ELLPACK, slice = 32 rows = one warp, column-major inside a slice) built once
 // from the host CSR; A and B share the column indices.  Lane r of a warp owns row 32*s+r, so every
 // value/index load is one fully coalesced 256 B / 128 B transaction; padding has value 0 and the row's
-// own column.  Algorithmic traffic: 12 B per stored entry + vectors = 200 B per row per SpMV for the
-// 15-entry rows of a Kuhn-split box mesh (HBM-bound; DESIGN.md "K4").
+// own column.  Row ownership is static: thread `tid` of the grid owns rows tid, tid+T, tid+2T, ... in
+// every phase of the solve, so everything a phase produces for its own row stays in shared memory (or
+// in thread-private global arrays for large meshes) and only the ONE vector that neighbour rows gather
+// (the search direction) is exchanged between CTAs.
 //
 // The whole solve (RHS, stimulus, initial residual, every CG iteration, convergence test) runs inside
-// one cooperative launch: grid = (CTAs that fit) with a generation-counting grid barrier, two barriers
-// per iteration.  Dot products are reduced per CTA, written to a partials array and summed by every CTA
-// in the same fixed order after the barrier, so all CTAs take the same branch on the convergence test
-// and the result is run-to-run deterministic.  No host round trip per iteration, no launch latency per
-// vector operation - which is what bounds the 58k-node Niederer slab.
-#include <cooperative_groups.h>
-
+// one cooperative launch of one 512-thread CTA per SM, and it contains NO memory fence and NO atomic:
+// measured on B200 (tests/cuda/sync_bench.cu) a gpu-scope fence costs about 1.2 us, so a classic
+// fence + flag barrier is 2.5 us (cooperative-groups grid.sync) to 6 us.  Instead every value that
+// crosses CTAs travels WITH its generation number in one aligned 16-byte store {double, uint64}
+// (the idea of NCCL's LL protocol):
+//   * the exchanged vector is an array of such pairs; a gather spins on the tag of the element it
+//     needs - dataflow synchronisation at element granularity, no barrier before the SpMV;
+//   * the dot products: every CTA publishes tagged partial sums, CTA 0 polls them (one record per
+//     thread), adds them in a fixed order and publishes tagged totals that everybody polls:
+//     1.9 us per reduction, bit-reproducible, and all CTAs see the same totals so they take the same
+//     branch on the convergence test.
+// Two buffers alternate for the exchanged vector; the reduction between two writes of the same buffer
+// is an all-to-all dependency, which is what makes the reuse safe (DESIGN.md "K4").
+//
+// Two Krylov drivers:
+//   pde_cg_kernel      KSPCG as PETSc runs it: two reductions per iteration.
+//   pde_pipecg_kernel  pipelined CG (Ghysels & Vanroose; PETSc's KSPPIPECG): mathematically the same
+//                      iterates, ONE reduction per iteration.
+// RESIDENT=true keeps the CG vectors of a CTA's rows in shared memory (up to 3072 rows per SM = 454k
+// rows per GPU); RESIDENT=false streams them from global memory (HBM-bound for large meshes).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "mono_ctx.h"
@@ -31,6 +47,12 @@ namespace {
 constexpr int kSlice = 32;
 constexpr int kPdeThreads = 512;
 constexpr int kWarpsPerBlock = kPdeThreads / 32;
+constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
+constexpr int kMaxResidentRows = 5;   // rows per thread whose CG vectors fit in shared memory (9 x 8 B each)
+constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
+constexpr unsigned kSpinLimit = 1u << 22;  // polls before a thread gives up on a peer (seconds)
+
+typedef unsigned long long u64;
 
 struct PdeArgs {
   int64_t n_owned, n_local, n_slices;
@@ -39,36 +61,38 @@ struct PdeArgs {
   const double* A;
   const double* B;
   const double* dinv;
-  double *x, *v_prev, *b, *r, *z, *p0, *p1, *q;
-  int n_stim;
-  const StimDev* stims;
-  double t_eval, dt;
+  const double* v_prev;
+  double* x;                        // solution (owned rows written here at the end)
+  double* work[8];                  // streaming mode: thread-private vectors (n_owned each)
+  SyncRec *t0, *t1;                 // the exchanged vector, tagged {value, generation}, two buffers of n_local
+  const double* stim_vec;           // dense sum_k a_k(t) s_k over owned rows (valid when has_stim)
+  int has_stim;
+  int rows_per_thread;              // ceil(n_slices / warps of the worker CTAs)
+  int n_workers;                    // CTAs 0 .. n_workers-1 own rows; CTA n_workers only reduces
+  double dt;
   double rtol, atol;
   int max_it, norm_type, x0_mode;
-  unsigned* bar;
-  double* partials;  // [2][4][gridDim.x]
+  SyncRec* recs;                    // partial sums [2 parities][4 slots][n_workers], then totals [2][4]
+  u64 gen0;                         // first generation number of this launch (monotonic across launches)
   KspResult* res;
+  u64* timeline;                    // optional (measurement): globaltimer stamps of CTA 0 at phase boundaries
 };
 
-// ---- grid-wide barrier (all CTAs are co-resident: cooperative launch) ---------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned* gen = bar + 1;
-    const unsigned g = *gen;
-    __threadfence();
-    if (atomicAdd(bar, 1u) == nblocks - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*gen == g) {
-      }
-    }
-    __threadfence();
+__device__ __forceinline__ void stamp(const PdeArgs& a, int& n) {
+  if (a.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 0 && n < 63) {
+    u64 t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.timeline[1 + n++] = t;
+    a.timeline[0] = (u64)n;
   }
-  __syncthreads();
 }
+
+struct Scratch {                    // static shared memory of the persistent kernels
+  double warp_part[4 * kWarpsPerBlock];
+  double totals[4];
+  double red[4 * kMaxBlocks];
+  int fail;
+};
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -76,226 +100,596 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Reduce NV per-thread values over the CTA and store the CTA's partial sums (slot-major) for this parity.
+// One aligned 16-byte store / load: value and tag always travel together.
+__device__ __forceinline__ void st_tag(SyncRec* p, double v, u64 g) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(g) : "memory");
+}
+
+__device__ __forceinline__ void ld_tag(const SyncRec* p, double& v, u64& g) {
+  long long a;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(g) : "l"(p) : "memory");
+  v = __longlong_as_double(a);
+}
+
+__device__ __forceinline__ double wait_tag(const SyncRec* p, u64 want, int* fail) {
+  double v;
+  u64 g;
+  unsigned spins = 0;
+  do {
+    ld_tag(p, v, g);
+  } while (g != want && ++spins < kSpinLimit);
+  if (g != want) *fail = 1;
+  return v;
+}
+
+// ---- grid-wide sums ------------------------------------------------------------------------------------------
+// Workers post tagged per-CTA partial sums and later wait for the tagged totals; the reducer CTA (which
+// owns no rows) polls all partial sums of a generation (one record per thread), adds them in a fixed order and
+// publishes the totals.  Work placed between post and wait overlaps the reduction.  `gen` is the same in
+// every CTA and increases by one per reduction; two record sets alternate on its parity (a worker cannot be
+// more than one reduction ahead of the slowest one: it needs a total that includes that worker's partial sum).
+__device__ __forceinline__ SyncRec* partial_recs(const PdeArgs& a, u64 gen) { return a.recs + (size_t)(gen & 1ull) * 4 * a.n_workers; }
+__device__ __forceinline__ SyncRec* total_recs(const PdeArgs& a, u64 gen) { return a.recs + (size_t)8 * a.n_workers + (gen & 1ull) * 4; }
+
 template <int NV>
-__device__ __forceinline__ void block_partials(const double (&v)[NV], double* partials, int parity, double* smem) {
+__device__ __forceinline__ void post(const double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const double s = warp_sum(v[k]);
-    if (lane == 0) smem[k * kWarpsPerBlock + warp] = s;
+    if (lane == 0) sh.warp_part[k * kWarpsPerBlock + warp] = s;
   }
   __syncthreads();
   if (warp == 0) {
+    SyncRec* part = partial_recs(a, gen);
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      double s = lane < kWarpsPerBlock ? smem[k * kWarpsPerBlock + lane] : 0.0;
+      double s = lane < kWarpsPerBlock ? sh.warp_part[k * kWarpsPerBlock + lane] : 0.0;
       s = warp_sum(s);
-      if (lane == 0) partials[((size_t)parity * 4 + k) * gridDim.x + blockIdx.x] = s;
+      if (lane == 0) st_tag(part + (size_t)k * a.n_workers + blockIdx.x, s, gen);
     }
   }
 }
 
-// After the barrier: every CTA sums all CTAs' partials in the same order -> identical totals everywhere.
 template <int NV>
-__device__ __forceinline__ void grid_totals(double (&out)[NV], const double* partials, int parity, double* smem) {
+__device__ __forceinline__ void wait(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
+  if (threadIdx.x < NV) sh.totals[threadIdx.x] = wait_tag(total_recs(a, gen) + threadIdx.x, gen, &sh.fail);
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = sh.totals[k];
+  __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void reduce_publish(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned nw = a.n_workers;
+  const SyncRec* part = partial_recs(a, gen);
+  for (unsigned idx = threadIdx.x; idx < NV * nw; idx += kPdeThreads) sh.red[idx] = wait_tag(part + idx, gen, &sh.fail);
+  __syncthreads();
   if (warp < NV) {
-    const volatile double* src = partials + ((size_t)parity * 4 + warp) * gridDim.x;
     double s = 0.0;
-    for (unsigned i = lane; i < gridDim.x; i += 32) s += src[i];
+    for (unsigned i = lane; i < nw; i += 32) s += sh.red[warp * nw + i];
     s = warp_sum(s);
-    if (lane == 0) smem[64 + warp] = s;
+    if (lane == 0) {
+      st_tag(total_recs(a, gen) + warp, s, gen);
+      sh.totals[warp] = s;
+    }
   }
   __syncthreads();
 #pragma unroll
-  for (int k = 0; k < NV; ++k) out[k] = smem[64 + k];
+  for (int k = 0; k < NV; ++k) v[k] = sh.totals[k];
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kPdeThreads, 1) pde_step_kernel(const PdeArgs a) {
-  __shared__ double smem[64 + 8];
-  const unsigned nb = gridDim.x;
-  const int lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  const int64_t warp_stride = (int64_t)nb * kWarpsPerBlock;
-  const int64_t tid = (int64_t)blockIdx.x * kPdeThreads + threadIdx.x;
-  const int64_t tstride = (int64_t)nb * kPdeThreads;
-  const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
-  int parity = 0;
-
-  // ---- K2: b = B v_   (and q = A v_ when the initial guess is v_) --------------------------------
-  for (int64_t s = warp_global; s < a.n_slices; s += warp_stride) {
-    const int64_t row = s * kSlice + lane;
-    const int64_t beg = a.slice_ptr[s];
-    const int width = (int)((a.slice_ptr[s + 1] - beg) / kSlice);
-    double accB = 0.0, accA = 0.0;
-    for (int k = 0; k < width; ++k) {
-      const int64_t e = beg + (int64_t)k * kSlice + lane;
-      const double vj = a.v_prev[a.cols[e]];
-      accB = fma(a.B[e], vj, accB);
-      if (x0_prev) accA = fma(a.A[e], vj, accA);
-    }
-    if (row < a.n_owned) {
-      a.b[row] = accB;
-      if (x0_prev) a.q[row] = accA;
-    }
-  }
-  // ---- stimulus: b += dt * a_k(t) * s_k for every stimulus whose window contains t ----------------
-  bool any_stim = false;
-  for (int k = 0; k < a.n_stim; ++k) {
-    const StimDev st = a.stims[k];
-    if (st.amp != 0.0 && a.t_eval >= st.t_start && a.t_eval <= st.t_end && st.nnz > 0) {
-      grid_barrier(a.bar, nb);  // rows of b are complete / previous stimulus applied
-      any_stim = true;
-      const double f = a.dt * st.amp;
-      for (int64_t e = tid; e < st.nnz; e += tstride) a.b[st.idx[e]] += f * st.val[e];
-    }
-  }
-  if (any_stim) grid_barrier(a.bar, nb);
-
-  // ---- initial residual, z = D^-1 r, p = z --------------------------------------------------------
-  {
-    double acc[3] = {0.0, 0.0, 0.0};  // r.z, norm^2 of r (chosen norm), norm^2 of b (chosen norm)
-    for (int64_t i = tid; i < a.n_owned; i += tstride) {
-      const double bi = a.b[i];
-      const double di = a.dinv[i];
-      double xi, ri;
-      if (x0_prev) {
-        xi = a.v_prev[i];
-        ri = bi - a.q[i];
-      } else {
-        xi = 0.0;
-        ri = bi;
-      }
-      const double zi = di * ri;
-      a.x[i] = xi;
-      a.r[i] = ri;
-      a.z[i] = zi;
-      a.p0[i] = zi;
-      acc[0] = fma(ri, zi, acc[0]);
-      const double zb = di * bi;
-      if (a.norm_type == MONO_NORM_PRECONDITIONED) {
-        acc[1] = fma(zi, zi, acc[1]);
-        acc[2] = fma(zb, zb, acc[2]);
-      } else if (a.norm_type == MONO_NORM_UNPRECONDITIONED) {
-        acc[1] = fma(ri, ri, acc[1]);
-        acc[2] = fma(bi, bi, acc[2]);
-      } else {
-        acc[1] = fma(ri, zi, acc[1]);
-        acc[2] = fma(bi, zb, acc[2]);
-      }
-    }
-    block_partials<3>(acc, a.partials, parity, smem);
-  }
-  grid_barrier(a.bar, nb);
-  double tot[3];
-  grid_totals<3>(tot, a.partials, parity, smem);
-  parity ^= 1;
-  double rz = tot[0];
-  double rnorm = sqrt(fabs(tot[1]));
-  const double bnorm = sqrt(fabs(tot[2]));
-  const double ttol = fmax(a.rtol * bnorm, a.atol);
-  int its = 0;
-  int reason = 0;
-  if (!(rnorm == rnorm)) {
-    reason = MONO_KSP_DIVERGED_NAN;
-  } else if (rnorm <= ttol) {
-    reason = rnorm <= a.atol ? MONO_KSP_CONVERGED_ATOL : MONO_KSP_CONVERGED_RTOL;
-  } else if (a.max_it <= 0) {
-    reason = MONO_KSP_DIVERGED_ITS;
-  }
-
-  // p_cur holds the search direction of the current iteration; for it >= 1 it is formed on the fly
-  // inside the SpMV gather as z + beta*p_old (both complete vectors), and written for the own row.
-  double* p_old = a.p0;
-  double* p_new = a.p1;
-  double beta = 0.0;
-  bool first = true;
-  while (reason == 0) {
-    // ---- K4a: q = A p, p.q -----------------------------------------------------------------------
-    double pq[1] = {0.0};
-    for (int64_t s = warp_global; s < a.n_slices; s += warp_stride) {
-      const int64_t row = s * kSlice + lane;
-      const int64_t beg = a.slice_ptr[s];
-      const int width = (int)((a.slice_ptr[s + 1] - beg) / kSlice);
-      double acc = 0.0;
-      if (first) {
-        for (int k = 0; k < width; ++k) {
-          const int64_t e = beg + (int64_t)k * kSlice + lane;
-          acc = fma(a.A[e], p_old[a.cols[e]], acc);
-        }
-        if (row < a.n_owned) {
-          a.q[row] = acc;
-          pq[0] = fma(p_old[row], acc, pq[0]);
-        }
-      } else {
-        for (int k = 0; k < width; ++k) {
-          const int64_t e = beg + (int64_t)k * kSlice + lane;
-          const int32_t j = a.cols[e];
-          acc = fma(a.A[e], fma(beta, p_old[j], a.z[j]), acc);
-        }
-        if (row < a.n_owned) {
-          const double pi = fma(beta, p_old[row], a.z[row]);
-          p_new[row] = pi;
-          a.q[row] = acc;
-          pq[0] = fma(pi, acc, pq[0]);
+// ---- SELL rows ---------------------------------------------------------------------------------------------
+// acc[m] = sum_k val(m, k) * g(col(k)) over the `width` entries of a row.  Entries are fetched in unrolled
+// batches of kChunk so the index loads, then the gathers, are all in flight together.  TAGGED: the gathered
+// vector is an array of {value, generation} pairs and the gather waits until every element carries `want`.
+template <int NM, bool TAGGED, class ColF, class ValF>
+__device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const void* vec, u64 want, int* fail, double (&acc)[NM]) {
+#pragma unroll
+  for (int m = 0; m < NM; ++m) acc[m] = 0.0;
+  for (int k0 = 0; k0 < width; k0 += kChunk) {
+    int32_t c[kChunk];
+    double g[kChunk];
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) c[u] = (k0 + u < width) ? col(k0 + u) : -1;
+    if constexpr (TAGGED) {
+      const SyncRec* tv = static_cast<const SyncRec*>(vec);
+      unsigned late = 0;
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) {
+        g[u] = 0.0;
+        if (c[u] >= 0) {
+          u64 t;
+          ld_tag(tv + c[u], g[u], t);
+          late |= (t != want ? 1u : 0u) << u;
         }
       }
+      if (late) {  // some producer is behind: wait for exactly those elements
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+          if (late & (1u << u)) g[u] = wait_tag(tv + c[u], want, fail);
+      }
+    } else {
+      const double* dv = static_cast<const double*>(vec);
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) g[u] = c[u] >= 0 ? __ldg(dv + c[u]) : 0.0;
     }
-    block_partials<1>(pq, a.partials, parity, smem);
-    grid_barrier(a.bar, nb);
-    double t1[1];
-    grid_totals<1>(t1, a.partials, parity, smem);
-    parity ^= 1;
-    if (!first) {
-      double* t = p_old;
-      p_old = p_new;
-      p_new = t;
-    }
-    first = false;
-    const double alpha = rz / t1[0];
-    // ---- K4b: x += alpha p ; r -= alpha q ; z = D^-1 r ; r.z and the residual norm ---------------
-    double acc[2] = {0.0, 0.0};
-    for (int64_t i = tid; i < a.n_owned; i += tstride) {
-      const double pi = p_old[i];
-      const double ri = fma(-alpha, a.q[i], a.r[i]);
-      const double zi = a.dinv[i] * ri;
-      a.x[i] = fma(alpha, pi, a.x[i]);
-      a.r[i] = ri;
-      a.z[i] = zi;
-      acc[0] = fma(ri, zi, acc[0]);
-      if (a.norm_type == MONO_NORM_PRECONDITIONED)
-        acc[1] = fma(zi, zi, acc[1]);
-      else if (a.norm_type == MONO_NORM_UNPRECONDITIONED)
-        acc[1] = fma(ri, ri, acc[1]);
-      else
-        acc[1] = fma(ri, zi, acc[1]);
-    }
-    block_partials<2>(acc, a.partials, parity, smem);
-    grid_barrier(a.bar, nb);
-    double t2[2];
-    grid_totals<2>(t2, a.partials, parity, smem);
-    parity ^= 1;
-    ++its;
-    rnorm = sqrt(fabs(t2[1]));
-    beta = t2[0] / rz;
-    rz = t2[0];
-    if (!(rnorm == rnorm) || !(alpha == alpha)) {
-      reason = MONO_KSP_DIVERGED_NAN;
-    } else if (rnorm <= ttol) {
-      reason = rnorm <= a.atol ? MONO_KSP_CONVERGED_ATOL : MONO_KSP_CONVERGED_RTOL;
-    } else if (its >= a.max_it) {
-      reason = MONO_KSP_DIVERGED_ITS;
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      double av[kChunk];
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) av[u] = (k0 + u < width) ? val(m, k0 + u) : 0.0;
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) acc[m] = fma(av[u], g[u], acc[m]);
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+}
+
+// A thread's view of one of its rows: where the row's entries are (global SELL storage, or the copy of the
+// A entries the thread made in shared memory at kernel start when it owns a single row).
+struct RowRef {
+  int64_t row, beg;
+  int width, lane, slot;
+};
+
+template <bool MATSMEM>
+struct MatA {
+  const PdeArgs& a;
+  const double* sa;    // [kChunk][kPdeThreads] A entries of the thread's row (MATSMEM)
+  const int32_t* sc;   // [kChunk][kPdeThreads] their columns
+  template <bool TAGGED>
+  __device__ __forceinline__ double apply(const RowRef& r, const void* vec, u64 want, int* fail) const {
+    double out[1];
+    if constexpr (MATSMEM) {
+      sell_row<1, TAGGED>(
+          r.width, [&](int k) { return sc[k * kPdeThreads + threadIdx.x]; },
+          [&](int, int k) { return sa[k * kPdeThreads + threadIdx.x]; }, vec, want, fail, out);
+    } else {
+      sell_row<1, TAGGED>(
+          r.width, [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); },
+          [&](int, int k) { return __ldg(a.A + r.beg + (int64_t)k * kSlice + r.lane); }, vec, want, fail, out);
+    }
+    return out[0];
+  }
+};
+
+// b = B v_ (+ dt * stimulus) and, for a non-zero initial guess x0 = v_, A x0 in the same pass.
+__device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool x0_prev, double& bi, double& ax0) {
+  int dummy = 0;
+  auto col = [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); };
+  if (x0_prev) {
+    double ab[2];
+    sell_row<2, false>(
+        r.width, col, [&](int m, int k) { return __ldg((m == 0 ? a.B : a.A) + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0,
+        &dummy, ab);
+    bi = ab[0];
+    ax0 = ab[1];
+  } else {
+    double b1[1];
+    sell_row<1, false>(
+        r.width, col, [&](int, int k) { return __ldg(a.B + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0, &dummy, b1);
+    bi = b1[0];
+    ax0 = 0.0;
+  }
+  if (a.has_stim && r.row < a.n_owned) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
+}
+
+__device__ __forceinline__ double norm_term(int norm_type, double r, double z) {
+  // summand of the squared residual norm: preconditioned ||M^-1 r||, unpreconditioned ||r||, natural r.M^-1 r
+  return norm_type == MONO_NORM_PRECONDITIONED ? z * z : (norm_type == MONO_NORM_UNPRECONDITIONED ? r * r : r * z);
+}
+
+__device__ __forceinline__ int classify(double rnorm, double ttol, double atol, int its, int max_it, bool nan_scalar) {
+  if (!(rnorm == rnorm) || nan_scalar) return MONO_KSP_DIVERGED_NAN;
+  if (rnorm <= ttol) return rnorm <= atol ? MONO_KSP_CONVERGED_ATOL : MONO_KSP_CONVERGED_RTOL;
+  if (its >= max_it) return MONO_KSP_DIVERGED_ITS;
+  return 0;
+}
+
+__device__ __forceinline__ void write_result(const PdeArgs& a, int its, int reason, double rnorm) {
+  if (threadIdx.x == 0) {
     a.res->iterations = its;
     a.res->reason = reason;
     a.res->rnorm = rnorm;
     a.res->total_iterations += its;
     a.res->solves += 1;
   }
+}
+
+// Thread-private CG vectors of the rows a thread owns: shared memory (RESIDENT) or global arrays.
+enum { VR = 0, VU, VW, VZ, VQ, VS, VP, VN, VX, NVEC };  // VX last: it aliases a.x in streaming mode
+
+template <bool RESIDENT>
+struct VecStore {
+  double* g[NVEC];
+  double* sm;
+  int cap;
+  __device__ __forceinline__ double ld(int v, const RowRef& r) const {
+    if constexpr (RESIDENT) return sm[v * cap + r.slot];
+    return __ldcg(g[v] + r.row);
+  }
+  __device__ __forceinline__ void st(int v, const RowRef& r, double val) const {
+    if constexpr (RESIDENT)
+      sm[v * cap + r.slot] = val;
+    else
+      __stcg(g[v] + r.row, val);
+  }
+};
+
+template <bool RESIDENT>
+__device__ __forceinline__ VecStore<RESIDENT> make_store(const PdeArgs& a, double* dyn_smem) {
+  VecStore<RESIDENT> V;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) V.g[k] = a.work[k];
+  V.g[VX] = a.x;
+  V.sm = dyn_smem;
+  V.cap = a.rows_per_thread * kPdeThreads;
+  return V;
+}
+
+// rows of this thread: slices warp_global, warp_global + warp_stride, ... (the same in every phase)
+template <bool MATSMEM>
+__device__ __forceinline__ bool load_row(const PdeArgs& a, RowRef& r, int64_t s, int lane, int slot, int width_cached) {
+  r.row = s * kSlice + lane;
+  r.lane = lane;
+  r.slot = slot;
+  if constexpr (MATSMEM) {
+    r.beg = 0;
+    r.width = width_cached;
+  } else {
+    r.beg = __ldg(a.slice_ptr + s);
+    r.width = (int)((__ldg(a.slice_ptr + s + 1) - r.beg) / kSlice);
+  }
+  return true;
+}
+
+#define OWN_ROWS_BEGIN                                                                                       \
+  {                                                                                                          \
+    int slot__ = threadIdx.x;                                                                                \
+    for (int64_t s__ = warp_global; s__ < a.n_slices; s__ += warp_stride, slot__ += kPdeThreads) {           \
+      RowRef r;                                                                                              \
+      load_row<MATSMEM>(a, r, s__, lane, slot__, width_cached);
+#define OWN_ROWS_END \
+  }                  \
+  }
+
+// Reducer CTA of the pipelined solver: follows the workers' sequence of reductions and decides convergence
+// exactly as they do (same totals, same arithmetic), then reports the result.
+__device__ void pipecg_reducer(const PdeArgs& a, Scratch& sh) {
+  u64 gen = a.gen0;
+  double bn[1];
+  reduce_publish<1>(bn, a, gen++, sh);
+  const double ttol = fmax(a.rtol * sqrt(fabs(bn[0])), a.atol);
+  int its = 0, reason = 0;
+  double rnorm = 0.0;
+  while (true) {
+    double acc[3];
+    reduce_publish<3>(acc, a, gen++, sh);
+    rnorm = sqrt(fabs(acc[2]));
+    reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(acc[0] == acc[0]) || !(acc[1] == acc[1]));
+    if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+    if (reason != 0) break;
+    ++its;
+  }
+  write_result(a, its, reason, rnorm);
+  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+}
+
+__device__ void cg_reducer(const PdeArgs& a, Scratch& sh) {
+  u64 gen = a.gen0;
+  double acc3[3];
+  reduce_publish<3>(acc3, a, gen++, sh);
+  double rnorm = sqrt(fabs(acc3[1]));
+  const double ttol = fmax(a.rtol * sqrt(fabs(acc3[2])), a.atol);
+  int its = 0;
+  int reason = classify(rnorm, ttol, a.atol, 0, a.max_it, false);
+  if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+  while (reason == 0) {
+    double pq[1], acc2[2];
+    reduce_publish<1>(pq, a, gen++, sh);
+    reduce_publish<2>(acc2, a, gen++, sh);
+    ++its;
+    rnorm = sqrt(fabs(acc2[1]));
+    reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(pq[0] == pq[0]) || pq[0] == 0.0);
+    if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+  }
+  write_result(a, its, reason, rnorm);
+  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+}
+
+// The A entries of the thread's single row -> shared memory (MATSMEM), once per launch.
+template <bool MATSMEM>
+__device__ __forceinline__ int stage_matrix(const PdeArgs& a, double* sa, int32_t* sc, int64_t warp_global, int lane) {
+  if constexpr (!MATSMEM) return 0;
+  int width = 0;
+  if (warp_global < a.n_slices) {
+    const int64_t beg = __ldg(a.slice_ptr + warp_global);
+    width = (int)((__ldg(a.slice_ptr + warp_global + 1) - beg) / kSlice);
+#pragma unroll
+    for (int k = 0; k < kChunk; ++k) {
+      const bool on = k < width;
+      sc[k * kPdeThreads + threadIdx.x] = on ? __ldg(a.cols + beg + (int64_t)k * kSlice + lane) : -1;
+      sa[k * kPdeThreads + threadIdx.x] = on ? __ldg(a.A + beg + (int64_t)k * kSlice + lane) : 0.0;
+    }
+  }
+  return width;
+}
+
+// ---- KSPCG (PETSc semantics): two reductions per iteration ------------------------------------------------
+//   q = A p ; alpha = (r,z)/(p,q) ; x += alpha p ; r -= alpha q ; z = M^-1 r ; beta = (r,z)_new/(r,z) ; p = z + beta p
+template <bool RESIDENT, bool MATSMEM>
+__global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a) {
+  extern __shared__ double dyn_smem[];
+  __shared__ Scratch sh;
+  if (threadIdx.x == 0) sh.fail = 0;
+  __syncthreads();
+  if (blockIdx.x == a.n_workers) {
+    cg_reducer(a, sh);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)a.n_workers * kWarpsPerBlock;
+  const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
+  u64 gen = a.gen0;   // reduction generations
+  u64 vtag = a.gen0;  // generation of the exchanged vector p
+  const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
+  double* sa = dyn_smem + (size_t)NVEC * V.cap;
+  int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
+  const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
+  const MatA<MATSMEM> Aop{a, sa, sc};
+
+  // ---- K2 + initial residual: r = b - A x0, z = D^-1 r, p = z ---------------------------------------------
+  double acc3[3] = {0.0, 0.0, 0.0};  // r.z, norm^2 of r, norm^2 of b (chosen norm)
+  OWN_ROWS_BEGIN
+    RowRef g = r;
+    if constexpr (MATSMEM) {
+      g.beg = __ldg(a.slice_ptr + s__);
+    }
+    double bi, ax0;
+    rhs_row(a, g, x0_prev, bi, ax0);
+    if (r.row < a.n_owned) {
+      const double di = __ldg(a.dinv + r.row);
+      const double ri = x0_prev ? bi - ax0 : bi;
+      const double zi = di * ri;
+      V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
+      V.st(VR, r, ri);
+      V.st(VP, r, zi);
+      st_tag(a.t0 + r.row, zi, vtag);
+      acc3[0] = fma(ri, zi, acc3[0]);
+      acc3[1] += norm_term(a.norm_type, ri, zi);
+      acc3[2] += norm_term(a.norm_type, bi, di * bi);
+    }
+  OWN_ROWS_END
+  post<3>(acc3, a, gen, sh);
+  wait<3>(acc3, a, gen++, sh);
+  double rz = acc3[0];
+  double rnorm = sqrt(fabs(acc3[1]));
+  const double ttol = fmax(a.rtol * sqrt(fabs(acc3[2])), a.atol);
+  int its = 0;
+  int reason = classify(rnorm, ttol, a.atol, 0, a.max_it, false);
+  if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+  SyncRec* p_cur = a.t0;
+  SyncRec* p_nxt = a.t1;
+  while (reason == 0) {
+    // ---- K4a: q = A p (gathers wait on the tag of each element), p.q ----------------------------------------
+    double pq[1] = {0.0};
+    OWN_ROWS_BEGIN
+      const double qi = Aop.template apply<true>(r, p_cur, vtag, &sh.fail);
+      if (r.row < a.n_owned) {
+        V.st(VQ, r, qi);
+        pq[0] = fma(V.ld(VP, r), qi, pq[0]);
+      }
+    OWN_ROWS_END
+    post<1>(pq, a, gen, sh);
+    wait<1>(pq, a, gen++, sh);
+    const double alpha = rz / pq[0];
+    // ---- K4b: x += alpha p ; r -= alpha q ; z = D^-1 r ; r.z and the residual norm (own rows) ------------------
+    double acc2[2] = {0.0, 0.0};
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) {
+        const double ri = fma(-alpha, V.ld(VQ, r), V.ld(VR, r));
+        const double zi = __ldg(a.dinv + r.row) * ri;
+        V.st(VX, r, fma(alpha, V.ld(VP, r), V.ld(VX, r)));
+        V.st(VR, r, ri);
+        acc2[0] = fma(ri, zi, acc2[0]);
+        acc2[1] += norm_term(a.norm_type, ri, zi);
+      }
+    OWN_ROWS_END
+    post<2>(acc2, a, gen, sh);
+    wait<2>(acc2, a, gen++, sh);
+    ++its;
+    rnorm = sqrt(fabs(acc2[1]));
+    const double beta = acc2[0] / rz;
+    rz = acc2[0];
+    reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(pq[0] == pq[0]) || pq[0] == 0.0);
+    if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+    if (reason != 0) break;
+    // ---- p = z + beta p (own rows), published with the next generation tag ------------------------------------
+    ++vtag;
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) {
+        const double pi = fma(beta, V.ld(VP, r), __ldg(a.dinv + r.row) * V.ld(VR, r));
+        V.st(VP, r, pi);
+        st_tag(p_nxt + r.row, pi, vtag);
+      }
+    OWN_ROWS_END
+    SyncRec* t = p_cur;
+    p_cur = p_nxt;
+    p_nxt = t;
+  }
+  if constexpr (RESIDENT) {
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) a.x[r.row] = V.ld(VX, r);
+    OWN_ROWS_END
+  }
+  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+}
+
+// ---- KSPPIPECG: one reduction per iteration, overlapped with the SpMV -----------------------------------------
+// Ghysels & Vanroose, "Hiding global synchronization latency in the preconditioned Conjugate Gradient
+// algorithm" (Alg. 3), as in PETSc's KSPPIPECG:
+//   gamma = (r,u) ; delta = (w,u) ; m = M^-1 w ; n = A m ; beta = gamma/gamma_old ;
+//   alpha = gamma / (delta - beta*gamma/alpha_old) ; z = n + beta z ; q = m + beta q ; s = w + beta s ;
+//   p = u + beta p ; x += alpha p ; r -= alpha s ; u -= alpha q ; w -= alpha z
+// Only m (and u once, at start-up) is gathered by neighbour rows.  The partial sums of gamma, delta are
+// posted BEFORE n = A m is computed and the totals are awaited after it.
+template <bool RESIDENT, bool MATSMEM>
+__global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArgs a) {
+  extern __shared__ double dyn_smem[];
+  __shared__ Scratch sh;
+  if (threadIdx.x == 0) sh.fail = 0;
+  __syncthreads();
+  if (blockIdx.x == a.n_workers) {
+    pipecg_reducer(a, sh);
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)a.n_workers * kWarpsPerBlock;
+  const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
+  u64 gen = a.gen0;
+  u64 vtag = a.gen0;
+  const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
+  double* sa = dyn_smem + (size_t)NVEC * V.cap;
+  int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
+  const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
+  const MatA<MATSMEM> Aop{a, sa, sc};
+  int nstamp = 0;
+  stamp(a, nstamp);
+
+  // ---- P0: b = B v_ (+ stimulus) ; r = b - A x0 ; u = D^-1 r -> t1 (tag vtag) --------------------------------
+  double bn[1] = {0.0};
+  OWN_ROWS_BEGIN
+    RowRef g = r;
+    if constexpr (MATSMEM) {
+      g.beg = __ldg(a.slice_ptr + s__);
+    }
+    double bi, ax0;
+    rhs_row(a, g, x0_prev, bi, ax0);
+    if (r.row < a.n_owned) {
+      const double di = __ldg(a.dinv + r.row);
+      const double ri = x0_prev ? bi - ax0 : bi;
+      const double ui = di * ri;
+      V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
+      V.st(VR, r, ri);
+      V.st(VU, r, ui);
+      st_tag(a.t1 + r.row, ui, vtag);
+      bn[0] += norm_term(a.norm_type, bi, di * bi);
+    }
+  OWN_ROWS_END
+  post<1>(bn, a, gen, sh);
+  stamp(a, nstamp);
+
+  // ---- P1: w = A u ; m = D^-1 w -> t0 (tag vtag+1) ; gamma, delta, norm (overlaps the reduction of |b|) ----------
+  double acc[3] = {0.0, 0.0, 0.0};
+  OWN_ROWS_BEGIN
+    const double wi = Aop.template apply<true>(r, a.t1, vtag, &sh.fail);
+    if (r.row < a.n_owned) {
+      const double ri = V.ld(VR, r), ui = V.ld(VU, r);
+      V.st(VW, r, wi);
+      st_tag(a.t0 + r.row, __ldg(a.dinv + r.row) * wi, vtag + 1);
+      acc[0] = fma(ri, ui, acc[0]);
+      acc[1] = fma(wi, ui, acc[1]);
+      acc[2] += norm_term(a.norm_type, ri, ui);
+    }
+  OWN_ROWS_END
+  ++vtag;
+  stamp(a, nstamp);
+  wait<1>(bn, a, gen++, sh);
+  const double ttol = fmax(a.rtol * sqrt(fabs(bn[0])), a.atol);
+  stamp(a, nstamp);
+
+  int its = 0, reason = 0;
+  double rnorm = 0.0, gamma_old = 1.0, alpha_old = 1.0;
+  SyncRec* m_cur = a.t0;
+  SyncRec* m_nxt = a.t1;
+  while (true) {
+    post<3>(acc, a, gen, sh);
+    stamp(a, nstamp);
+    // n = A m while the reduction is in flight
+    OWN_ROWS_BEGIN
+      const double ni = Aop.template apply<true>(r, m_cur, vtag, &sh.fail);
+      if (r.row < a.n_owned) V.st(VN, r, ni);
+    OWN_ROWS_END
+    stamp(a, nstamp);
+    wait<3>(acc, a, gen++, sh);
+    stamp(a, nstamp);
+    const double gamma = acc[0], delta = acc[1];
+    rnorm = sqrt(fabs(acc[2]));
+    reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(gamma == gamma) || !(delta == delta));
+    if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+    if (reason != 0) break;
+    const bool first = its == 0;
+    const double beta = first ? 0.0 : gamma / gamma_old;
+    const double alpha = first ? gamma / delta : gamma / (delta - beta * gamma / alpha_old);
+    acc[0] = acc[1] = acc[2] = 0.0;
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) {
+        const double di = __ldg(a.dinv + r.row);
+        double xi = V.ld(VX, r), ri = V.ld(VR, r), ui = V.ld(VU, r), wi = V.ld(VW, r);
+        const double mi = di * wi;
+        double zi = V.ld(VN, r), qi = mi, si = wi, pi = ui;
+        if (!first) {
+          zi = fma(beta, V.ld(VZ, r), zi);
+          qi = fma(beta, V.ld(VQ, r), qi);
+          si = fma(beta, V.ld(VS, r), si);
+          pi = fma(beta, V.ld(VP, r), pi);
+        }
+        xi = fma(alpha, pi, xi);
+        ri = fma(-alpha, si, ri);
+        ui = fma(-alpha, qi, ui);
+        wi = fma(-alpha, zi, wi);
+        V.st(VZ, r, zi);
+        V.st(VQ, r, qi);
+        V.st(VS, r, si);
+        V.st(VP, r, pi);
+        V.st(VX, r, xi);
+        V.st(VR, r, ri);
+        V.st(VU, r, ui);
+        V.st(VW, r, wi);
+        st_tag(m_nxt + r.row, di * wi, vtag + 1);
+        acc[0] = fma(ri, ui, acc[0]);
+        acc[1] = fma(wi, ui, acc[1]);
+        acc[2] += norm_term(a.norm_type, ri, ui);
+      }
+    OWN_ROWS_END
+    ++vtag;
+    SyncRec* t = m_cur;
+    m_cur = m_nxt;
+    m_nxt = t;
+    gamma_old = gamma;
+    alpha_old = alpha;
+    ++its;
+  }
+  if constexpr (RESIDENT) {
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) a.x[r.row] = V.ld(VX, r);
+    OWN_ROWS_END
+  }
+  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+}
+
+// measurement: `n` back-to-back reductions (cost of one grid-wide reduction of 3 scalars)
+__global__ void __launch_bounds__(kPdeThreads, 1) sync_bench_kernel(const PdeArgs a, int n, double* out) {
+  __shared__ Scratch sh;
+  if (threadIdx.x == 0) sh.fail = 0;
+  __syncthreads();
+  u64 gen = a.gen0;
+  double v[3] = {1.0, 2.0, 3.0};
+  for (int i = 0; i < n; ++i) {
+    if (blockIdx.x == a.n_workers) {
+      reduce_publish<3>(v, a, gen++, sh);
+    } else {
+      post<3>(v, a, gen, sh);
+      wait<3>(v, a, gen++, sh);
+    }
+    v[0] = v[0] * 1e-3 + 1.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = v[0] + sh.fail;
 }
 
 // ---- K3: A = C_m*Mass + dt*theta*K ; B = C_m*Mass - dt*(1-theta)*K ; Jacobi diagonal ------------------
@@ -328,6 +722,18 @@ __global__ void jacobi_kernel(int64_t n_owned, int64_t n_slices, const int64_t* 
       if (cols[e] == row) d += A[e];
     }
     dinv[row] = 1.0 / d;
+  }
+}
+
+// stim_vec[idx[e]] (+)= scale * val[e]   (scale == 0: clear the entries of a stimulus that went inactive)
+__global__ void stim_scatter_kernel(int64_t nnz, const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                    double scale, double* __restrict__ stim_vec) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
+    if (scale == 0.0)
+      stim_vec[idx[e]] = 0.0;
+    else
+      atomicAdd(stim_vec + idx[e], scale * val[e]);
   }
 }
 
@@ -379,6 +785,8 @@ int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, c
   }
   c->n_slices = ns;
   c->sell_nnz = tot;
+  c->max_width = 0;
+  for (int64_t s = 0; s < ns; ++s) c->max_width = std::max<int>(c->max_width, (int)((sp[s + 1] - sp[s]) / kSlice));
   MONO_CUDA(c, cudaMalloc(&c->slice_ptr, (ns + 1) * sizeof(int64_t)));
   MONO_CUDA(c, cudaMalloc(&c->cols, std::max<int64_t>(tot, 1) * sizeof(int32_t)));
   for (double** p : {&c->mass, &c->stiff, &c->A, &c->B}) MONO_CUDA(c, cudaMalloc(p, std::max<int64_t>(tot, 1) * sizeof(double)));
@@ -409,31 +817,98 @@ int pde_update_matrices(mono_ctx* c, double dt) {
   return MONO_OK;
 }
 
+template <class K>
+static bool opt_in_smem(K kernel, size_t bytes) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess) return true;
+  (void)cudaGetLastError();
+  return false;
+}
+
 int pde_setup_launch_config(mono_ctx* c) {
-  int per_sm = 0;
-  MONO_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pde_step_kernel, kPdeThreads, 0));
-  if (per_sm < 1) return mono_fail(c, MONO_E_CUDA, "pde_step_kernel does not fit on an SM");
-  // one CTA per SM (16 warps): enough loads in flight for HBM, cheapest barrier
+  // worker CTAs own rows (one CTA per SM: 16 warps, 16 entries per row in flight each); one more CTA only
+  // reduces the dot products
   const int64_t need = (c->n_slices + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  c->pde_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(need, c->n_sm));
+  c->pde_workers = (int)std::max<int64_t>(1, std::min<int64_t>(need, std::min(c->n_sm, kMaxBlocks) - 1));
+  c->pde_blocks = c->pde_workers + 1;
   c->pde_threads = kPdeThreads;
-  if (c->partials) cudaFree(c->partials);
-  MONO_CUDA(c, cudaMalloc(&c->partials, sizeof(double) * 2 * 4 * c->pde_blocks));
-  MONO_CUDA(c, cudaMemsetAsync(c->partials, 0, sizeof(double) * 2 * 4 * c->pde_blocks, c->stream));
+  c->rows_per_thread = (int)std::max<int64_t>(
+      1, (c->n_slices + (int64_t)c->pde_workers * kWarpsPerBlock - 1) / ((int64_t)c->pde_workers * kWarpsPerBlock));
+  if (c->recs) cudaFree(c->recs);
+  const size_t nrec = (size_t)8 * c->pde_workers + 8;  // partial sums [2][4][workers] + totals [2][4]
+  MONO_CUDA(c, cudaMalloc(&c->recs, sizeof(SyncRec) * nrec));
+  MONO_CUDA(c, cudaMemsetAsync(c->recs, 0, sizeof(SyncRec) * nrec, c->stream));
+  c->sync_gen = 1;
+  // the exchanged vector: two tagged buffers over owned + ghost dofs (tag 0 = never written)
+  const int64_t nl = std::max<int64_t>(c->n_local, 32);
+  for (SyncRec** t : {&c->t0, &c->t1}) {
+    if (*t) cudaFree(*t);
+    MONO_CUDA(c, cudaMalloc(t, sizeof(SyncRec) * nl));
+    MONO_CUDA(c, cudaMemsetAsync(*t, 0, sizeof(SyncRec) * nl, c->stream));
+  }
+  // shared-memory residency: the CG vectors of a CTA's rows, and (one row per thread) the A entries too
+  const bool force_stream = getenv("MONO_PDE_STREAM") != nullptr;
+  c->resident = c->rows_per_thread <= kMaxResidentRows && !force_stream;
+  c->matsmem = c->resident && c->rows_per_thread == 1 && c->max_width <= kChunk && getenv("MONO_PDE_NO_MATSMEM") == nullptr;
+  c->resident_smem = c->resident ? (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double) : 0;
+  if (c->matsmem) c->resident_smem += (size_t)kChunk * kPdeThreads * (sizeof(double) + sizeof(int32_t));
+  if (c->matsmem && !(opt_in_smem(pde_pipecg_kernel<true, true>, c->resident_smem) && opt_in_smem(pde_cg_kernel<true, true>, c->resident_smem))) {
+    c->matsmem = false;
+    c->resident_smem = (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double);
+  }
+  if (c->resident && !c->matsmem &&
+      !(opt_in_smem(pde_pipecg_kernel<true, false>, c->resident_smem) && opt_in_smem(pde_cg_kernel<true, false>, c->resident_smem))) {
+    c->resident = false;
+    c->resident_smem = 0;
+  }
+  return MONO_OK;
+}
+
+static const void* pde_kernel_for(const mono_ctx* c) {
+  const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
+  if (c->matsmem) return pipe ? (const void*)pde_pipecg_kernel<true, true> : (const void*)pde_cg_kernel<true, true>;
+  if (c->resident) return pipe ? (const void*)pde_pipecg_kernel<true, false> : (const void*)pde_cg_kernel<true, false>;
+  return pipe ? (const void*)pde_pipecg_kernel<false, false> : (const void*)pde_cg_kernel<false, false>;
+}
+
+static int stim_refresh(mono_ctx* c, double t_eval, int* has_stim) {
+  // The dense source vector sum_k a_k(t) s_k only changes when a window opens/closes or an amplitude is
+  // re-assigned; rebuild it then (before the step kernel, stream-ordered), not inside the solve.
+  std::vector<std::pair<int, double>> sig;
+  for (int k = 0; k < (int)c->stims_host.size(); ++k) {
+    const StimDev& st = c->stims_host[k];
+    if (st.amp != 0.0 && t_eval >= st.t_start && t_eval <= st.t_end && st.nnz > 0) sig.emplace_back(k, st.amp);
+  }
+  if (sig != c->stim_sig) {
+    if (!c->stim_vec) {
+      const int64_t nl = std::max<int64_t>(c->n_local, 32);
+      MONO_CUDA(c, cudaMalloc(&c->stim_vec, sizeof(double) * nl));
+      MONO_CUDA(c, cudaMemsetAsync(c->stim_vec, 0, sizeof(double) * nl, c->stream));
+    }
+    const int threads = 256;
+    auto launch = [&](const StimDev& st, double scale) {
+      const int blocks = (int)std::min<int64_t>((st.nnz + threads - 1) / threads, (int64_t)c->n_sm * 8);
+      stim_scatter_kernel<<<blocks, threads, 0, c->stream>>>(st.nnz, st.idx, st.val, scale, c->stim_vec);
+      c->launches++;
+    };
+    for (auto& kv : c->stim_sig) launch(c->stims_host[kv.first], 0.0);
+    for (auto& kv : sig) launch(c->stims_host[kv.first], kv.second);
+    MONO_CUDA(c, cudaGetLastError());
+    c->stim_sig = sig;
+  }
+  *has_stim = sig.empty() ? 0 : 1;
   return MONO_OK;
 }
 
 int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
-  if (c->stims_dirty) {
-    const int n = (int)c->stims_host.size();
-    if (n > c->stims_dev_cap) {
-      if (c->stims_dev) cudaFree(c->stims_dev);
-      c->stims_dev_cap = std::max(n, 8);
-      MONO_CUDA(c, cudaMalloc(&c->stims_dev, sizeof(StimDev) * c->stims_dev_cap));
+  int has_stim = 0;
+  int rc = stim_refresh(c, t_eval, &has_stim);
+  if (rc) return rc;
+  if (!c->resident && !c->work[0]) {  // streaming mode: thread-private vectors live in global memory
+    const int64_t no = std::max<int64_t>(c->n_owned, 32);
+    for (double*& p : c->work) {
+      MONO_CUDA(c, cudaMalloc(&p, sizeof(double) * no));
+      MONO_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * no, c->stream));
     }
-    if (n > 0)
-      MONO_CUDA(c, cudaMemcpyAsync(c->stims_dev, c->stims_host.data(), sizeof(StimDev) * n, cudaMemcpyHostToDevice, c->stream));
-    c->stims_dirty = false;
   }
   PdeArgs a;
   a.n_owned = c->n_owned;
@@ -444,29 +919,57 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   a.A = c->A;
   a.B = c->B;
   a.dinv = c->dinv;
-  a.x = c->x;
   a.v_prev = c->v_prev;
-  a.b = c->b;
-  a.r = c->r;
-  a.z = c->z;
-  a.p0 = c->p0;
-  a.p1 = c->p1;
-  a.q = c->q;
-  a.n_stim = (int)c->stims_host.size();
-  a.stims = c->stims_dev;
-  a.t_eval = t_eval;
+  a.x = c->x;
+  for (int k = 0; k < 8; ++k) a.work[k] = c->work[k];
+  a.t0 = c->t0;
+  a.t1 = c->t1;
+  a.stim_vec = c->stim_vec;
+  a.has_stim = has_stim;
+  a.rows_per_thread = c->rows_per_thread;
+  a.n_workers = c->pde_workers;
   a.dt = dt;
   a.rtol = c->rtol;
   a.atol = c->atol;
   a.max_it = c->max_it;
   a.norm_type = c->norm_type;
   a.x0_mode = c->x0_mode;
-  a.bar = c->bar;
-  a.partials = c->partials;
+  a.recs = c->recs;
+  a.gen0 = c->sync_gen;
   a.res = c->ksp_dev;
+  a.timeline = c->timeline_dev;
+  c->sync_gen += 3ull * (unsigned long long)std::max(c->max_it, 0) + 16ull;
   void* args[] = {&a};
-  MONO_CUDA(c, cudaLaunchCooperativeKernel((void*)pde_step_kernel, dim3(c->pde_blocks), dim3(c->pde_threads), args, 0, c->stream));
+  MONO_CUDA(c, cudaLaunchCooperativeKernel(pde_kernel_for(c), dim3(c->pde_blocks), dim3(c->pde_threads), args, c->resident_smem, c->stream));
   c->launches++;
+  return MONO_OK;
+}
+
+int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync) {
+  if (!c->recs) return mono_fail(c, MONO_E_INVALID, "set matrices first (the synchronisation records belong to the PDE stage)");
+  PdeArgs a{};
+  a.timeline = nullptr;
+  a.n_workers = c->pde_workers;
+  a.recs = c->recs;
+  a.gen0 = c->sync_gen;
+  c->sync_gen += (unsigned long long)n + 16ull;
+  double* out = nullptr;
+  MONO_CUDA(c, cudaMalloc(&out, sizeof(double)));
+  cudaEvent_t e0, e1;
+  MONO_CUDA(c, cudaEventCreate(&e0));
+  MONO_CUDA(c, cudaEventCreate(&e1));
+  void* args[] = {&a, &n, &out};
+  MONO_CUDA(c, cudaEventRecord(e0, c->stream));
+  MONO_CUDA(c, cudaLaunchCooperativeKernel((void*)sync_bench_kernel, dim3(c->pde_blocks), dim3(c->pde_threads), args, 0, c->stream));
+  MONO_CUDA(c, cudaEventRecord(e1, c->stream));
+  MONO_CUDA(c, cudaEventSynchronize(e1));
+  float ms = 0.f;
+  MONO_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  c->launches++;
+  if (us_per_sync) *us_per_sync = ms * 1e3f / (float)n;
   return MONO_OK;
 }
 

@@ -51,6 +51,9 @@ extern "C" {
 #define MONO_NORM_PRECONDITIONED 0 /* PETSc default for KSPCG: ||M^-1 r||_2 */
 #define MONO_NORM_UNPRECONDITIONED 1
 #define MONO_NORM_NATURAL 2        /* sqrt(r . M^-1 r) */
+#define MONO_KSP_CG 0     /* PETSc KSPCG: two global reductions per iteration */
+#define MONO_KSP_PIPECG 1 /* PETSc KSPPIPECG (Ghysels-Vanroose pipelined CG): same iterates in exact arithmetic,
+                             one global synchronisation per iteration */
 #define MONO_X0_ZERO 0             /* PETSc default (KSPSetInitialGuessNonzero false) */
 #define MONO_X0_PREVIOUS 1         /* start from v_ ; fewer iterations, same fixed point */
 
@@ -125,6 +128,8 @@ int mono_pde_set_matrices(mono_ctx *ctx, int64_t n_owned, int64_t n_ghost, const
  * (petsc_options ksp_rtol / ksp_atol / ksp_max_it / pc_type / ksp_norm_type).                      */
 int mono_pde_config(mono_ctx *ctx, double C_m, double theta, double rtol, double atol, int max_it,
                     int pc_type, int norm_type, int x0_mode);
+/* Krylov driver (petsc_options ksp_type "cg" | "pipecg"); default MONO_KSP_CG. */
+int mono_pde_set_ksp_type(mono_ctx *ctx, int ksp_type);
 /* (Re)build A = C_m*Mass + dt*theta*K and B = C_m*Mass - dt*(1-theta)*K; called by mono_pde_step
  * itself when |dt - current| >= 1e-12 (base_model.py:225-230, _update_matrices :188-194).          */
 int mono_pde_set_dt(mono_ctx *ctx, double dt);
@@ -184,6 +189,12 @@ int mono_stage_times_ms(mono_ctx *ctx, double *ms2, int64_t *steps, int reset);
 int mono_stage_timing(mono_ctx *ctx, int enable);
 /* fp64 FMA micro-benchmark (the denominator of the ODE-stage roofline): achieved DFMA TFLOP/s */
 int mono_bench_dfma(mono_ctx *ctx, double *tflops);
+/* cost of one in-kernel grid-wide synchronisation + reduction of the persistent PDE kernel, in us
+ * (n back-to-back synchronisations in one cooperative launch; needs the PDE matrices to be set) */
+int mono_bench_grid_sync(mono_ctx *ctx, int n, float *us_per_sync);
+/* measurement: with enable != 0 the persistent PDE kernel records %globaltimer (ns) of CTA 0 at its phase
+ * boundaries; stamps64[0] = count, stamps64[1..] = the stamps of the last launch (synchronises). */
+int mono_debug_timeline(mono_ctx *ctx, int enable, uint64_t *stamps64);
 /* number of kernel launches issued by this context so far */
 int mono_launch_count(mono_ctx *ctx, int64_t *launches);
 

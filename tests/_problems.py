@@ -1,4 +1,5 @@
 """Shared problem builders for the tests (oracle side: meshes, matrices, Niederer constants)."""
+import functools
 import importlib
 
 import numpy as np
@@ -17,6 +18,7 @@ def niederer_conductivities():
     return sl / chi_per_m * 1e3, st / chi_per_m * 1e3
 
 
+@functools.lru_cache(maxsize=4)
 def niederer_slab(dx: float, L=(20.0, 7.0, 3.0)):
     n = tuple(int(np.rint(l / dx)) for l in L)
     pts, cells = fem.box_mesh(n, (0, 0, 0), L)

@@ -68,22 +68,27 @@ def test_ode_per_node_parameters(ctx_factory, tag):
     ctx.close()
 
 
-def _pde_ctx(ctx_factory, prob, theta=0.5, rtol=1e-13, x0=0, pc=1, norm=0, max_it=1000):
+def _pde_ctx(ctx_factory, prob, theta=0.5, rtol=1e-13, x0=0, pc=1, norm=0, max_it=1000, ksp=0):
     ctx = ctx_factory()
     mass, stiff = prob["mass"], prob["stiff"]
     n = mass.shape[0]
     ctx.pde_set_matrices(n, 0, mass.indptr, mass.indices, mass.data, stiff.data)
     ctx.pde_config(prob["C_m"], theta, rtol, 1e-50, max_it, pc, norm, x0)
+    ctx.pde_set_ksp_type(ksp)
     return ctx
 
 
+KSP = {"cg": 0, "pipecg": 1}
+
+
+@pytest.mark.parametrize("ksp", ["cg", "pipecg"])
 @pytest.mark.parametrize("x0", [0, 1])
-def test_pde_single_step_tight(ctx_factory, x0):
+def test_pde_single_step_tight(ctx_factory, x0, ksp):
     prob = P.niederer_slab(0.5)
     n = prob["mass"].shape[0]
     rng = np.random.default_rng(3)
     v_prev = -85.0 + 120.0 * rng.random(n)
-    ctx = _pde_ctx(ctx_factory, prob, x0=x0)
+    ctx = _pde_ctx(ctx_factory, prob, x0=x0, ksp=KSP[ksp], rtol=1e-13 if ksp == "cg" else 1e-12)
     idx = np.nonzero(prob["stim_load"])[0]
     ctx.stim_add(idx, prob["stim_load"][idx], 0.0, 2.0, prob["stim_amp"])
     ctx.set_v_prev(v_prev)
@@ -101,24 +106,56 @@ def test_pde_single_step_tight(ctx_factory, x0):
     ctx.close()
 
 
-def test_pde_matches_petsc_style_cg_iteration_count(ctx_factory):
-    """Same algorithm, same tolerance -> same iteration count and the same iterate as the oracle's KSPCG restatement."""
+@pytest.mark.parametrize("ksp", ["cg", "pipecg"])
+@pytest.mark.parametrize("norm", [0, 1, 2])
+def test_pde_matches_petsc_style_cg_iteration_count(ctx_factory, ksp, norm):
+    """Same algorithm, same tolerance -> same iteration count and the same iterate as the oracle's KSPCG
+    restatement (pipelined CG produces the same iterates up to rounding)."""
     prob = P.niederer_slab(0.5)
     n = prob["mass"].shape[0]
     rng = np.random.default_rng(5)
     v_prev = -85.0 + 120.0 * rng.random(n)
-    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-5)
+    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-5, ksp=KSP[ksp], norm=norm)
     ctx.set_v_prev(v_prev)
     ctx.pde_step(0.0, 0.05)
     got = ctx.get_v(np.empty(n))
     its, rnorm, reason = ctx.ksp_info()
-    ref = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [], C_m=prob["C_m"], theta=0.5, solver="cg-jacobi", rtol=1e-5)
+    ref = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [], C_m=prob["C_m"], theta=0.5, solver="cg-jacobi", rtol=1e-5,
+                                  norm=["preconditioned", "unpreconditioned", "natural"][norm])
     ref.v_[:] = v_prev
     ref.step((0.0, 0.05))
     assert its == ref.ksp["iterations"], (its, ref.ksp)
     assert reason == ref.ksp["reason"]
     assert abs(rnorm - ref.ksp["residual_norm"]) <= 1e-6 * ref.ksp["residual_norm"]
-    assert np.abs(got - ref.state).max() <= 1e-10 * np.abs(ref.state).max()
+    assert np.abs(got - ref.state).max() <= 1e-9 * np.abs(ref.state).max()
+    ctx.close()
+
+
+@pytest.mark.parametrize("ksp,stream", [("cg", False), ("cg", True), ("pipecg", False), ("pipecg", True)])
+def test_pde_two_rows_per_thread(ctx_factory, ksp, stream, monkeypatch):
+    """132k-row slab: every thread of the persistent kernel owns two rows (shared-memory resident and
+    streaming variants of the pipelined solver), stimulus active, against the oracle's tight PCG."""
+    if stream:
+        monkeypatch.setenv("MONO_PDE_STREAM", "1")
+    prob = P.niederer_slab(0.15)
+    n = prob["mass"].shape[0]
+    assert n > 148 * 512
+    rng = np.random.default_rng(17)
+    v_prev = -85.0 + 120.0 * rng.random(n)
+    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-12, ksp=KSP[ksp])
+    idx = np.nonzero(prob["stim_load"])[0]
+    ctx.stim_add(idx, prob["stim_load"][idx], 0.0, 2.0, prob["stim_amp"])
+    ctx.set_v_prev(v_prev)
+    ref = om_mono.MonodomainModel(prob["mass"], prob["stiff"], [om_mono.Stimulus.window(prob["stim_load"], 0.0, 2.0, prob["stim_amp"])],
+                                  C_m=prob["C_m"], theta=0.5, solver="cg-jacobi", rtol=1e-13)
+    ref.v_[:] = v_prev
+    for t0, t1 in ((0.5, 0.51), (2.5, 2.51)):  # stimulus on, then off (the dense source vector is cleared)
+        ctx.pde_step(t0, t1)
+        ref.step((t0, t1))
+        got = ctx.get_v(np.empty(n))
+        its, rnorm, reason = ctx.ksp_info()
+        assert reason > 0, (its, rnorm, reason)
+        assert np.abs(got - ref.state).max() <= 1e-9 * np.abs(ref.state).max()
     ctx.close()
 
 
@@ -143,8 +180,9 @@ def test_pde_dt_change_rebuilds_matrices(ctx_factory):
     ctx.close()
 
 
+@pytest.mark.parametrize("ksp", ["cg", "pipecg"])
 @pytest.mark.parametrize("theta_split", [1.0, 0.5])
-def test_split_steps_niederer_small(ctx_factory, theta_split):
+def test_split_steps_niederer_small(ctx_factory, theta_split, ksp):
     """A few fused split steps (TP06 GRL1 + CN diffusion + S1 stimulus) against the oracle's literal
     restatement of MonodomainSplittingSolver.step."""
     import beat_b200.models.tp06 as hm
@@ -160,7 +198,7 @@ def test_split_steps_niederer_small(ctx_factory, theta_split):
                             num_states=len(y0), v_index=om.state_index("V"))
     ref = om_mono.SplittingSolver(pde, ode, theta=theta_split)
 
-    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-12)
+    ctx = _pde_ctx(ctx_factory, prob, rtol=1e-12, ksp=KSP[ksp])
     idx = np.nonzero(prob["stim_load"])[0]
     ctx.stim_add(idx, prob["stim_load"][idx], 0.0, 2.0, prob["stim_amp"])
     ctx.ode_create(1, 1, n, om.state_index("V"), len(y0))

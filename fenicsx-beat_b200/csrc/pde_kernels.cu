@@ -48,7 +48,7 @@ constexpr int kSlice = 32;
 constexpr int kPdeThreads = 512;
 constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
-constexpr int kMaxResidentRows = 5;   // rows per thread whose CG vectors fit in shared memory (9 x 8 B each)
+constexpr int kMaxResidentRows = 5;   // rows per thread whose CG vectors fit in shared memory (10 x 8 B each)
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
 constexpr unsigned kSpinLimit = 1u << 22;  // polls before a thread gives up on a peer (seconds)
 
@@ -300,7 +300,7 @@ __device__ __forceinline__ void write_result(const PdeArgs& a, int its, int reas
 }
 
 // Thread-private CG vectors of the rows a thread owns: shared memory (RESIDENT) or global arrays.
-enum { VR = 0, VU, VW, VZ, VQ, VS, VP, VN, VX, NVEC };  // VX last: it aliases a.x in streaming mode
+enum { VR = 0, VU, VW, VZ, VQ, VS, VP, VN, VX, VD, NVEC };  // streaming mode: VX aliases a.x, VD aliases a.dinv
 
 template <bool RESIDENT>
 struct VecStore {
@@ -325,6 +325,7 @@ __device__ __forceinline__ VecStore<RESIDENT> make_store(const PdeArgs& a, doubl
 #pragma unroll
   for (int k = 0; k < 8; ++k) V.g[k] = a.work[k];
   V.g[VX] = a.x;
+  V.g[VD] = const_cast<double*>(a.dinv);
   V.sm = dyn_smem;
   V.cap = a.rows_per_thread * kPdeThreads;
   return V;
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     rhs_row(a, g, x0_prev, bi, ax0);
     if (r.row < a.n_owned) {
       const double di = __ldg(a.dinv + r.row);
+      if constexpr (RESIDENT) V.st(VD, r, di);
       const double ri = x0_prev ? bi - ax0 : bi;
       const double zi = di * ri;
       V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     OWN_ROWS_BEGIN
       if (r.row < a.n_owned) {
         const double ri = fma(-alpha, V.ld(VQ, r), V.ld(VR, r));
-        const double zi = __ldg(a.dinv + r.row) * ri;
+        const double zi = V.ld(VD, r) * ri;
         V.st(VX, r, fma(alpha, V.ld(VP, r), V.ld(VX, r)));
         V.st(VR, r, ri);
         acc2[0] = fma(ri, zi, acc2[0]);
@@ -512,7 +514,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     ++vtag;
     OWN_ROWS_BEGIN
       if (r.row < a.n_owned) {
-        const double pi = fma(beta, V.ld(VP, r), __ldg(a.dinv + r.row) * V.ld(VR, r));
+        const double pi = fma(beta, V.ld(VP, r), V.ld(VD, r) * V.ld(VR, r));
         V.st(VP, r, pi);
         st_tag(p_nxt + r.row, pi, vtag);
       }
@@ -572,6 +574,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
     rhs_row(a, g, x0_prev, bi, ax0);
     if (r.row < a.n_owned) {
       const double di = __ldg(a.dinv + r.row);
+      if constexpr (RESIDENT) V.st(VD, r, di);
       const double ri = x0_prev ? bi - ax0 : bi;
       const double ui = di * ri;
       V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
@@ -591,7 +594,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
     if (r.row < a.n_owned) {
       const double ri = V.ld(VR, r), ui = V.ld(VU, r);
       V.st(VW, r, wi);
-      st_tag(a.t0 + r.row, __ldg(a.dinv + r.row) * wi, vtag + 1);
+      st_tag(a.t0 + r.row, V.ld(VD, r) * wi, vtag + 1);
       acc[0] = fma(ri, ui, acc[0]);
       acc[1] = fma(wi, ui, acc[1]);
       acc[2] += norm_term(a.norm_type, ri, ui);
@@ -629,7 +632,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
     acc[0] = acc[1] = acc[2] = 0.0;
     OWN_ROWS_BEGIN
       if (r.row < a.n_owned) {
-        const double di = __ldg(a.dinv + r.row);
+        const double di = V.ld(VD, r);
         double xi = V.ld(VX, r), ri = V.ld(VR, r), ui = V.ld(VU, r), wi = V.ld(VW, r);
         const double mi = di * wi;
         double zi = V.ld(VN, r), qi = mi, si = wi, pi = ui;

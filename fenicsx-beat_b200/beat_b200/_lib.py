@@ -33,6 +33,7 @@ SIGNATURES = {
     "mono_comm_unique_id": (C.c_int, [C.c_void_p]),
     "mono_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "mono_set_halo": (C.c_int, [C.c_void_p, C.c_int, c_int32_p, c_int32_p, c_int32_p, c_int32_p]),
+    "mono_halo_refresh_nccl": (C.c_int, [C.c_void_p]),
     "mono_ode_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int]),
     "mono_ode_set_states": (C.c_int, [C.c_void_p, c_double_p, C.c_int64]),
     "mono_ode_get_states": (C.c_int, [C.c_void_p, c_double_p, C.c_int64]),
@@ -88,6 +89,24 @@ class MonoError(RuntimeError):
     pass
 
 
+def _point_at_bundled_nccl() -> None:
+    """The library dlopens NCCL lazily (mono_comm_init).  When the process has not loaded torch's bundled
+    libnccl.so.2 yet, tell it where that copy lives so both end up on the same NCCL."""
+    if os.environ.get("MONO_NCCL_LIB"):
+        return
+    import importlib.util
+
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+        cand = os.path.join(base, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["MONO_NCCL_LIB"] = cand
+            return
+
+
 def load_library():
     """dlopen the C ABI and attach signatures.  Raises if the library was not built."""
     global _lib
@@ -98,6 +117,7 @@ def load_library():
             f"{LIB_PATH} not found: build it with `python fenicsx-beat_b200/build.py` "
             "(or __graft_entry__.build()).  There is no CPU fallback."
         )
+    _point_at_bundled_nccl()
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)
@@ -210,6 +230,9 @@ class Context:
     def comm_init(self, nranks: int, rank: int, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self._ck(self.lib.mono_comm_init(self.h, nranks, rank, buf))
+
+    def halo_refresh_nccl(self):
+        self._ck(self.lib.mono_halo_refresh_nccl(self.h))
 
     def set_halo(self, nbr_ranks, send_ptr, send_idx, recv_ptr):
         nbr = np.ascontiguousarray(nbr_ranks, dtype=np.int32)

@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or force or not os.path.exists(OUT):
-        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-lnccl"]
+        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-ldl"]  # NCCL is dlopen'ed at mono_comm_init (halo.cu)
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -1,28 +1,92 @@
-// K5: ghost-dof exchange between ranks (one rank per GPU).
+// K5: everything that crosses ranks (one rank per GPU, one process per rank).
 //
-// Replaces the MPI neighbourhood exchanges hidden in the reference's PDE step:
+// Replaces the MPI traffic hidden in the reference's PDE step:
 //   b.ghostUpdate(ADD, REVERSE)   src/beat/base_model.py:203-206  -> not needed: the device RHS is an SpMV
 //                                   over OWNED rows with ghost columns of v_ already valid (K1 runs on
 //                                   ghosts too, as the reference's ODE stage does, odesolver.py:189-190)
-//   state.x.scatter_forward()     src/beat/base_model.py:242       -> halo_refresh(x)
-//   MatMult scatter inside KSP    (PETSc, inside :236)              -> per-iteration halo of the CG vectors
-//   MPI_Allreduce inside KSP      (PETSc, inside :236)              -> cross-rank reduction of the CG scalars
+//   MatMult scatter inside KSP    (PETSc, inside :236)              -> per-iteration exchange of the CG vector
+//   MPI_Allreduce inside KSP      (PETSc, inside :236)              -> cross-rank sums of the CG scalars
+//   state.x.scatter_forward()     src/beat/base_model.py:242       -> ghost refresh of the solution
 //
-// Communication backend: NCCL point-to-point (ncclSend/ncclRecv grouped per neighbour) over NVLink.
+// Data path: NOT a collective library call.  Every rank exports ONE allocation (the two tagged exchange
+// buffers, the x landing zone and the cross-rank reduction records, pde_kernels.cu) with CUDA IPC; the
+// neighbours map it, and the persistent PDE kernel stores boundary values and partial sums straight into
+// the peers' memory over NVLink ({value, generation} in one 16-byte store), so the halo exchange and the
+// all-reduce happen inside the solve, element by element, overlapped with the SpMV of the interior rows.
+// This file does the set-up for that: it exchanges the IPC handles and the ghost-block layout of all ranks
+// (one ncclAllGather at mono_set_halo time) and builds the send table.  NCCL is only the bootstrap (and the
+// reference exchange the tests compare the in-kernel path with, halo_refresh); it is loaded with dlopen at
+// mono_comm_init so that the library has no link-time NCCL dependency (the process may already hold torch's
+// bundled NCCL, which must be the one that is used).
+#include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "mono_ctx.h"
 
-#define MONO_NCCL(c, call)                                                                     \
-  do {                                                                                         \
-    ncclResult_t r__ = (call);                                                                 \
-    if (r__ != ncclSuccess)                                                                    \
-      return mono_fail((c), MONO_E_NCCL, std::string(#call) + ": " + ncclGetErrorString(r__)); \
-  } while (0)
-
 namespace {
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  std::string error;
+};
+
+NcclApi g_nccl;
+
+// Resolution order: a libnccl.so.2 the process already holds (torch's bundled one when the caller imported
+// torch), then $MONO_NCCL_LIB, then the default search path.
+bool nccl_load() {
+  if (g_nccl.handle) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) {
+    const char* env = getenv("MONO_NCCL_LIB");
+    if (env && *env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+  }
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    g_nccl.error = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return false;
+  }
+  bool ok = true;
+  auto sym = [&](const char* name) {
+    void* p = dlsym(h, name);
+    if (!p) {
+      ok = false;
+      g_nccl.error = std::string("libnccl.so.2 lacks ") + name;
+    }
+    return p;
+  };
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+  g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(sym("ncclGroupStart"));
+  g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
+  g_nccl.Send = reinterpret_cast<decltype(g_nccl.Send)>(sym("ncclSend"));
+  g_nccl.Recv = reinterpret_cast<decltype(g_nccl.Recv)>(sym("ncclRecv"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
+  if (!ok) return false;
+  g_nccl.handle = h;
+  return true;
+}
+
+#define MONO_NCCL(c, call)                                                                              \
+  do {                                                                                                  \
+    ncclResult_t r__ = (call);                                                                          \
+    if (r__ != ncclSuccess)                                                                             \
+      return mono_fail((c), MONO_E_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r__));      \
+  } while (0)
 
 __global__ void pack_kernel(int64_t n, const int32_t* __restrict__ idx, const double* __restrict__ vec,
                             double* __restrict__ out) {
@@ -30,16 +94,33 @@ __global__ void pack_kernel(int64_t n, const int32_t* __restrict__ idx, const do
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = vec[idx[i]];
 }
 
+// what every rank tells every other rank at mono_set_halo time
+struct PeerMeta {
+  cudaIpcMemHandle_t handle;   // of the rank's exchange allocation
+  int64_t n_owned, n_ghost;
+  int64_t off_t1, off_xg, off_xrecs, n_recs;  // layout of that allocation, in 16-byte records
+  int64_t ghost_off[kMaxRanks];  // where the ghosts owned by rank q start in this rank's ghost block (-1: none)
+  int64_t ghost_cnt[kMaxRanks];
+};
+
 }  // namespace
 
 int halo_destroy(mono_ctx* c) {
+  for (int q = 0; q < kMaxRanks; ++q) {
+    if (c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+    c->peer_base[q] = nullptr;
+    c->peer_xrecs[q] = nullptr;
+  }
+  c->peers_ready = false;
   if (c->comm) {
-    ncclCommDestroy((ncclComm_t)c->comm);
+    g_nccl.CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
   }
   return MONO_OK;
 }
 
+// Reference exchange through NCCL point-to-point (tests compare the in-kernel exchange against it; host-set
+// vectors whose ghosts the caller did not fill can be completed with it).
 int halo_refresh(mono_ctx* c, double* vec) {
   if (c->nranks <= 1 || c->n_nbr == 0) return MONO_OK;
   if (!c->comm) return mono_fail(c, MONO_E_INVALID, "multi-rank context without communicator (mono_comm_init)");
@@ -51,15 +132,15 @@ int halo_refresh(mono_ctx* c, double* vec) {
     MONO_CUDA(c, cudaGetLastError());
   }
   ncclComm_t comm = (ncclComm_t)c->comm;
-  MONO_NCCL(c, ncclGroupStart());
+  MONO_NCCL(c, g_nccl.GroupStart());
   for (int k = 0; k < c->n_nbr; ++k) {
     const int64_t ns = c->send_ptr[k + 1] - c->send_ptr[k];
     const int64_t nr = c->recv_ptr[k + 1] - c->recv_ptr[k];
-    if (ns > 0) MONO_NCCL(c, ncclSend(c->send_buf + c->send_ptr[k], ns, ncclDouble, c->nbr_ranks[k], comm, c->stream));
+    if (ns > 0) MONO_NCCL(c, g_nccl.Send(c->send_buf + c->send_ptr[k], ns, ncclDouble, c->nbr_ranks[k], comm, c->stream));
     if (nr > 0)
-      MONO_NCCL(c, ncclRecv(vec + c->n_owned + c->recv_ptr[k], nr, ncclDouble, c->nbr_ranks[k], comm, c->stream));
+      MONO_NCCL(c, g_nccl.Recv(vec + c->n_owned + c->recv_ptr[k], nr, ncclDouble, c->nbr_ranks[k], comm, c->stream));
   }
-  MONO_NCCL(c, ncclGroupEnd());
+  MONO_NCCL(c, g_nccl.GroupEnd());
   c->launches++;
   return MONO_OK;
 }
@@ -68,26 +149,30 @@ extern "C" {
 
 int mono_comm_unique_id(void* id_out128) {
   static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id is 128 bytes");
+  if (!nccl_load()) return mono_fail(nullptr, MONO_E_NCCL, g_nccl.error);
   ncclUniqueId id;
-  ncclResult_t r = ncclGetUniqueId(&id);
-  if (r != ncclSuccess) return mono_fail(nullptr, MONO_E_NCCL, std::string("ncclGetUniqueId: ") + ncclGetErrorString(r));
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != ncclSuccess) return mono_fail(nullptr, MONO_E_NCCL, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
   memcpy(id_out128, &id, sizeof(id));
   return MONO_OK;
 }
 
 int mono_comm_init(mono_ctx* c, int nranks, int rank, const void* id128) {
   MONO_CHECK(c, nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+  MONO_CHECK(c, nranks <= kMaxRanks, "more ranks than one node holds GPUs (kMaxRanks)");
   MONO_CHECK(c, c->comm == nullptr, "communicator already initialised");
   c->nranks = nranks;
   c->rank = rank;
   if (nranks == 1) return MONO_OK;
+  if (!nccl_load()) return mono_fail(c, MONO_E_NCCL, g_nccl.error);
   MONO_CUDA(c, cudaSetDevice(c->device));
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   ncclComm_t comm;
-  MONO_NCCL(c, ncclCommInitRank(&comm, nranks, id, rank));
+  MONO_NCCL(c, g_nccl.CommInitRank(&comm, nranks, id, rank));
   c->comm = (ncclComm*)comm;
-  MONO_CUDA(c, cudaMalloc(&c->red_buf, sizeof(double) * 8));
+  c->spin_timeout_ms = std::max(c->spin_timeout_ms, 30000.0);  // ranks reach their first step at different times
+  if (const char* e = getenv("MONO_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1.0, atof(e));
   return MONO_OK;
 }
 
@@ -102,6 +187,8 @@ int mono_set_halo(mono_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_
   MONO_CHECK(c, c->recv_ptr[n_nbr] == c->n_ghost, "recv_ptr must cover exactly the ghost block");
   c->n_send = c->send_ptr[n_nbr];
   for (int64_t k = 0; k < c->n_send; ++k) MONO_CHECK(c, send_idx[k] >= 0 && send_idx[k] < c->n_owned, "send index is not an owned dof");
+  for (int k = 0; k < n_nbr; ++k)
+    MONO_CHECK(c, nbr_ranks[k] >= 0 && nbr_ranks[k] < c->nranks && nbr_ranks[k] != c->rank, "bad neighbour rank");
   if (c->send_idx_dev) cudaFree(c->send_idx_dev);
   if (c->send_buf) cudaFree(c->send_buf);
   c->send_idx_dev = nullptr;
@@ -112,7 +199,86 @@ int mono_set_halo(mono_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_
     MONO_CUDA(c, cudaMemcpyAsync(c->send_idx_dev, send_idx, sizeof(int32_t) * c->n_send, cudaMemcpyHostToDevice, c->stream));
     MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  if (c->nranks <= 1) return MONO_OK;
+  MONO_CHECK(c, c->comm != nullptr, "mono_comm_init first");
+
+  // ---- tell everybody where our exchange allocation is and how our ghost block is laid out ---------------------
+  PeerMeta mine{};
+  MONO_CUDA(c, cudaIpcGetMemHandle(&mine.handle, c->exch));
+  mine.n_owned = c->n_owned;
+  mine.n_ghost = c->n_ghost;
+  mine.off_t1 = c->exch_off_t1;
+  mine.off_xg = c->exch_off_xg;
+  mine.off_xrecs = c->exch_off_xrecs;
+  mine.n_recs = c->exch_recs;
+  for (int q = 0; q < kMaxRanks; ++q) {
+    mine.ghost_off[q] = -1;
+    mine.ghost_cnt[q] = 0;
+  }
+  for (int k = 0; k < n_nbr; ++k) {
+    mine.ghost_off[nbr_ranks[k]] = recv_ptr[k];
+    mine.ghost_cnt[nbr_ranks[k]] = recv_ptr[k + 1] - recv_ptr[k];
+  }
+  std::vector<PeerMeta> all((size_t)c->nranks);
+  char *dsend = nullptr, *drecv = nullptr;
+  MONO_CUDA(c, cudaMalloc(&dsend, sizeof(PeerMeta)));
+  MONO_CUDA(c, cudaMalloc(&drecv, sizeof(PeerMeta) * c->nranks));
+  MONO_CUDA(c, cudaMemcpyAsync(dsend, &mine, sizeof(PeerMeta), cudaMemcpyHostToDevice, c->stream));
+  MONO_NCCL(c, g_nccl.AllGather(dsend, drecv, sizeof(PeerMeta), ncclChar, (ncclComm_t)c->comm, c->stream));
+  c->launches++;
+  MONO_CUDA(c, cudaMemcpyAsync(all.data(), drecv, sizeof(PeerMeta) * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(dsend);
+  cudaFree(drecv);
+
+  // ---- map every other rank's allocation (reduction records: all ranks; ghost slots: neighbours) ---------------
+  for (int q = 0; q < c->nranks; ++q) {
+    if (q == c->rank) continue;
+    if (c->peer_base[q]) {
+      cudaIpcCloseMemHandle(c->peer_base[q]);
+      c->peer_base[q] = nullptr;
+    }
+    cudaError_t e = cudaIpcOpenMemHandle(&c->peer_base[q], all[q].handle, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      c->peer_base[q] = nullptr;
+      return mono_fail(c, MONO_E_CUDA,
+                       "cudaIpcOpenMemHandle(rank " + std::to_string(q) + "): " + cudaGetErrorString(e) +
+                           " (the multi-GPU path needs peer access between the GPUs of the node)");
+    }
+    c->peer_xrecs[q] = static_cast<SyncRec*>(c->peer_base[q]) + all[q].off_xrecs;
+  }
+  c->peer_xrecs[c->rank] = c->xrecs;
+
+  // ---- send table: the i-th value we send to neighbour q lands in the i-th ghost q holds from us -----------------
+  std::vector<int32_t> rows;
+  std::vector<void*> d0, d1, dx;
+  for (int k = 0; k < n_nbr; ++k) {
+    const int q = nbr_ranks[k];
+    const int64_t cnt = send_ptr[k + 1] - send_ptr[k];
+    if (all[q].ghost_cnt[c->rank] != cnt)
+      return mono_fail(c, MONO_E_INVALID,
+                       "halo mismatch: this rank sends " + std::to_string(cnt) + " dofs to rank " + std::to_string(q) +
+                           " but that rank holds " + std::to_string(all[q].ghost_cnt[c->rank]) + " ghosts owned by it");
+    SyncRec* base = static_cast<SyncRec*>(c->peer_base[q]);
+    for (int64_t i = 0; i < cnt; ++i) {
+      const int64_t g = all[q].ghost_off[c->rank] + i;  // index in q's ghost block
+      rows.push_back(send_idx[send_ptr[k] + i]);
+      d0.push_back(base + all[q].n_owned + g);
+      d1.push_back(base + all[q].off_t1 + all[q].n_owned + g);
+      dx.push_back(base + all[q].off_xg + g);
+    }
+  }
+  int rc = pde_build_send_table(c, rows, d0, d1, dx);
+  if (rc) return rc;
+  c->peers_ready = true;
   return MONO_OK;
+}
+
+/* Ghost refresh of the PDE solution through NCCL send/recv (reference exchange; the step itself refreshes the
+ * ghosts inside the persistent kernel).  Collective over the neighbours. */
+int mono_halo_refresh_nccl(mono_ctx* c) {
+  MONO_CHECK(c, c->has_pde, "no PDE matrices");
+  return halo_refresh(c, c->x);
 }
 
 }  // extern "C"

@@ -153,7 +153,8 @@ int mono_ctx_destroy(mono_ctx* c) {
   for (void* p : {(void*)c->states, (void*)c->v_ode, (void*)c->params_dev, (void*)c->slice_ptr, (void*)c->cols,
                   (void*)c->mass, (void*)c->stiff, (void*)c->A, (void*)c->B, (void*)c->dinv, (void*)c->x,
                   (void*)c->v_prev, (void*)c->work[0], (void*)c->work[1], (void*)c->work[2], (void*)c->work[3],
-                  (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->t0, (void*)c->t1, (void*)c->stim_vec,
+                  (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->stim_vec,
+                  (void*)c->gen_state, (void*)c->send_of_row_dev, (void*)c->send_ents_dev,
                   (void*)c->recs, (void*)c->timeline_dev,
                   (void*)c->ksp_dev, (void*)c->probes_dev,
                   (void*)c->probe_vals_dev, (void*)c->probe_act_dev, (void*)c->flush_buf, (void*)c->send_idx_dev,
@@ -168,7 +169,8 @@ int mono_ctx_destroy(mono_ctx* c) {
   for (auto ev : c->marks)
     if (ev) cudaEventDestroy(ev);
 
-  halo_destroy(c);
+  halo_destroy(c);  // closes the peer mappings; must precede freeing our own exported allocation
+  if (c->exch) cudaFree(c->exch);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return MONO_OK;
@@ -444,9 +446,8 @@ static int pde_step_impl(mono_ctx* c, double t0, double t1) {
     int rc = pde_update_matrices(c, dt);
     if (rc) return rc;
   }
-  int rc = pde_launch_step(c, t, dt);
-  if (rc) return rc;
-  return halo_refresh(c, c->x);  // state.x.scatter_forward(), base_model.py:242
+  // the kernel also refreshes the ghosts of x (state.x.scatter_forward(), base_model.py:242) before it ends
+  return pde_launch_step(c, t, dt);
 }
 
 int mono_pde_step(mono_ctx* c, double t0, double t1) {

@@ -35,6 +35,8 @@ struct alignas(16) SyncRec {
   unsigned long long gen;
 };
 
+constexpr int kMaxRanks = 16;  // ranks of one multi-GPU run (one node)
+
 struct ProbeDev {
   int n;           // nodes in this probe (<= 4)
   int32_t node[4];
@@ -79,7 +81,20 @@ struct mono_ctx {
   double* dinv = nullptr;                // 1/diag(A) (or 1 for PC none), n_owned
   double *x = nullptr, *v_prev = nullptr;  // solution and previous solution, n_local each
   double* work[8] = {};                    // thread-private CG vectors in global memory (streaming mode only, lazy)
+  // everything a peer rank writes into lives in ONE allocation (exported with CUDA IPC): see pde_setup_launch_config
+  SyncRec* exch = nullptr;
+  int64_t exch_recs = 0, exch_off_t1 = 0, exch_off_xg = 0, exch_off_xrecs = 0;  // offsets in records
   SyncRec *t0 = nullptr, *t1 = nullptr;    // the exchanged CG vector, tagged {value, generation}, n_local each
+  SyncRec* xg = nullptr;                   // landing zone of the neighbours' final x values (n_ghost)
+  SyncRec* xrecs = nullptr;                // cross-rank reduction records [2][4][kMaxRanks]
+  unsigned long long* gen_state = nullptr; // device-resident generation counter of the persistent kernels
+  double spin_timeout_ms = 4000.0;         // a poll that waits longer flags the launch as failed
+  // peers (filled by mono_set_halo when nranks > 1)
+  bool peers_ready = false;
+  void* peer_base[kMaxRanks] = {};         // cudaIpcOpenMemHandle mappings of the other ranks' `exch`
+  SyncRec* peer_xrecs[kMaxRanks] = {};
+  int32_t* send_of_row_dev = nullptr;      // n_owned: first send entry of a row, -1 for interior rows
+  void* send_ents_dev = nullptr;           // SendEnt[n_send] (pde_kernels.cu)
   int ksp_type = MONO_KSP_CG;
   double C_m = 1.0, theta = 0.5, rtol = 1e-5, atol = 1e-50;
   int max_it = 10000, pc_type = MONO_PC_JACOBI, norm_type = MONO_NORM_PRECONDITIONED, x0_mode = MONO_X0_ZERO;
@@ -92,7 +107,6 @@ struct mono_ctx {
 
   // grid synchronisation records of the persistent PDE kernel: 2 parities x 4 scalars x blocks
   SyncRec* recs = nullptr;
-  unsigned long long sync_gen = 1;  // next unused generation number (monotonic over the context's life)
   int pde_blocks = 0, pde_workers = 0, pde_threads = 0, rows_per_thread = 1, max_width = 0;
   unsigned long long* timeline_dev = nullptr;  // measurement: phase time stamps of the last PDE kernel (64 slots)
   bool matsmem = false;             // ... and so do the A entries (one row per thread)
@@ -155,6 +169,9 @@ int pde_setup_launch_config(mono_ctx* c);
 int probes_launch(mono_ctx* c, double t0);
 int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync);
 
+int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<void*>& dst_t0,
+                         const std::vector<void*>& dst_t1, const std::vector<void*>& dst_xg);
+
 // halo.cu
-int halo_refresh(mono_ctx* c, double* vec);  // owner -> ghost copy of an n_local vector (no-op for 1 rank)
+int halo_refresh(mono_ctx* c, double* vec);  // owner -> ghost copy of an n_local vector through NCCL (no-op for 1 rank)
 int halo_destroy(mono_ctx* c);

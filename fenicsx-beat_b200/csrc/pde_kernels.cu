@@ -50,9 +50,15 @@ constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
 constexpr int kMaxResidentRows = 5;   // rows per thread whose CG vectors fit in shared memory (10 x 8 B each)
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
-constexpr unsigned kSpinLimit = 1u << 22;  // polls before a thread gives up on a peer (seconds)
-
 typedef unsigned long long u64;
+
+// where one owned boundary value goes on ONE neighbour rank (peer-mapped addresses of its ghost slot)
+struct SendEnt {
+  SyncRec* t[2];
+  SyncRec* xg;
+  int32_t next;  // next entry of the same row (a dof can be a ghost on several ranks), -1 ends the list
+  int32_t pad;
+};
 
 struct PdeArgs {
   int64_t n_owned, n_local, n_slices;
@@ -64,7 +70,7 @@ struct PdeArgs {
   const double* v_prev;
   double* x;                        // solution (owned rows written here at the end)
   double* work[8];                  // streaming mode: thread-private vectors (n_owned each)
-  SyncRec *t0, *t1;                 // the exchanged vector, tagged {value, generation}, two buffers of n_local
+  SyncRec* tb[2];                   // the exchanged vector, tagged {value, generation}, two buffers of n_local
   const double* stim_vec;           // dense sum_k a_k(t) s_k over owned rows (valid when has_stim)
   int has_stim;
   int rows_per_thread;              // ceil(n_slices / warps of the worker CTAs)
@@ -73,7 +79,15 @@ struct PdeArgs {
   double rtol, atol;
   int max_it, norm_type, x0_mode;
   SyncRec* recs;                    // partial sums [2 parities][4 slots][n_workers], then totals [2][4]
-  u64 gen0;                         // first generation number of this launch (monotonic across launches)
+  u64* gen_state;                   // [0] next unused generation number (device-resident: continues across launches,
+                                    //     so every rank of a multi-GPU run counts the same generations)
+  u64 spin_ns;                      // a poll gives up after this long (a peer died): the launch reports an error
+  // ---- multi-GPU (one rank per GPU; peers' buffers are mapped with CUDA IPC, stores travel over NVLink) ----
+  int nranks, rank;
+  SyncRec* xg;                      // landing zone of the neighbours' final x values (n_ghost, tagged)
+  SyncRec* peer_xrecs[kMaxRanks];   // every rank's cross-rank reduction records [2 parities][4 slots][nranks]
+  const int32_t* send_of_row;       // owned row -> first entry of its send list (-1: interior row)
+  const SendEnt* send_ents;
   KspResult* res;
   u64* timeline;                    // optional (measurement): globaltimer stamps of CTA 0 at phase boundaries
 };
@@ -100,34 +114,64 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// One aligned 16-byte store / load: value and tag always travel together.
+// One aligned 16-byte store / load: value and tag always travel together.  SYS = system scope: the location
+// is written or read by another GPU (peer-mapped memory over NVLink; a 16-byte store is one NVLink flit).
+template <bool SYS = false>
 __device__ __forceinline__ void st_tag(SyncRec* p, double v, u64 g) {
-  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(g) : "memory");
+  if constexpr (SYS)
+    asm volatile("st.relaxed.sys.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(g) : "memory");
+  else
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(g) : "memory");
 }
 
+template <bool SYS = false>
 __device__ __forceinline__ void ld_tag(const SyncRec* p, double& v, u64& g) {
   long long a;
-  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(g) : "l"(p) : "memory");
+  if constexpr (SYS)
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(g) : "l"(p) : "memory");
+  else
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(g) : "l"(p) : "memory");
   v = __longlong_as_double(a);
 }
 
-__device__ __forceinline__ double wait_tag(const SyncRec* p, u64 want, int* fail) {
+__device__ __forceinline__ u64 global_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Poll until the element carries `want`.  Gives up after spin_ns (checked every 256 polls) and flags the launch.
+template <bool SYS = false>
+__device__ __forceinline__ double wait_tag(const SyncRec* p, u64 want, int* fail, u64 spin_ns) {
   double v;
   u64 g;
+  ld_tag<SYS>(p, v, g);
+  if (g == want) return v;
+  const u64 t_begin = global_ns();
   unsigned spins = 0;
-  do {
-    ld_tag(p, v, g);
-  } while (g != want && ++spins < kSpinLimit);
-  if (g != want) *fail = 1;
+  while (true) {
+    ld_tag<SYS>(p, v, g);
+    if (g == want) return v;
+    if ((++spins & 255u) == 0u) {
+      if (*(volatile int*)fail) break;  // somebody already gave up: do not wait out the limit again
+      if (global_ns() - t_begin > spin_ns) break;
+    }
+  }
+  *fail = 1;
   return v;
 }
 
-// ---- grid-wide sums ------------------------------------------------------------------------------------------
+// ---- grid-wide (and rank-wide) sums ---------------------------------------------------------------------------
 // Workers post tagged per-CTA partial sums and later wait for the tagged totals; the reducer CTA (which
 // owns no rows) polls all partial sums of a generation (one record per thread), adds them in a fixed order and
 // publishes the totals.  Work placed between post and wait overlaps the reduction.  `gen` is the same in
-// every CTA and increases by one per reduction; two record sets alternate on its parity (a worker cannot be
-// more than one reduction ahead of the slowest one: it needs a total that includes that worker's partial sum).
+// every CTA (and on every rank) and increases by one per reduction; two record sets alternate on its parity (a
+// worker cannot be more than one reduction ahead of the slowest one: it needs a total that includes that
+// worker's partial sum; the same argument holds between ranks because the counter continues across launches).
+// MULTI: the reducer of every rank stores its rank-local sums into the cross-rank records of ALL ranks (peer
+// stores over NVLink), polls its own copy until all ranks have arrived and adds them in rank order: every rank
+// gets bit-identical totals, so all ranks take the same branch on the convergence test - an all-reduce without
+// a collective call and without leaving the kernel.
 __device__ __forceinline__ SyncRec* partial_recs(const PdeArgs& a, u64 gen) { return a.recs + (size_t)(gen & 1ull) * 4 * a.n_workers; }
 __device__ __forceinline__ SyncRec* total_recs(const PdeArgs& a, u64 gen) { return a.recs + (size_t)8 * a.n_workers + (gen & 1ull) * 4; }
 
@@ -153,24 +197,33 @@ __device__ __forceinline__ void post(const double (&v)[NV], const PdeArgs& a, u6
 
 template <int NV>
 __device__ __forceinline__ void wait(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
-  if (threadIdx.x < NV) sh.totals[threadIdx.x] = wait_tag(total_recs(a, gen) + threadIdx.x, gen, &sh.fail);
+  if (threadIdx.x < NV) sh.totals[threadIdx.x] = wait_tag(total_recs(a, gen) + threadIdx.x, gen, &sh.fail, a.spin_ns);
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = sh.totals[k];
   __syncthreads();
 }
 
-template <int NV>
+template <int NV, bool MULTI>
 __device__ __forceinline__ void reduce_publish(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned nw = a.n_workers;
   const SyncRec* part = partial_recs(a, gen);
-  for (unsigned idx = threadIdx.x; idx < NV * nw; idx += kPdeThreads) sh.red[idx] = wait_tag(part + idx, gen, &sh.fail);
+  for (unsigned idx = threadIdx.x; idx < NV * nw; idx += kPdeThreads) sh.red[idx] = wait_tag(part + idx, gen, &sh.fail, a.spin_ns);
   __syncthreads();
   if (warp < NV) {
     double s = 0.0;
     for (unsigned i = lane; i < nw; i += 32) s += sh.red[warp * nw + i];
     s = warp_sum(s);
+    if constexpr (MULTI) {
+      // lane q hands this rank's sum of slot `warp` to rank q, then collects rank q's sum from the local copy
+      const size_t slot = ((size_t)(gen & 1ull) * 4 + warp) * a.nranks;
+      if (lane < a.nranks) st_tag<true>(a.peer_xrecs[lane] + slot + a.rank, s, gen);
+      double mine = 0.0;
+      if (lane < a.nranks) mine = wait_tag<true>(a.peer_xrecs[a.rank] + slot + lane, gen, &sh.fail, a.spin_ns);
+      s = 0.0;
+      for (int q = 0; q < a.nranks; ++q) s += __shfl_sync(0xffffffffu, mine, q);  // rank order: same bits everywhere
+    }
     if (lane == 0) {
       st_tag(total_recs(a, gen) + warp, s, gen);
       sh.totals[warp] = s;
@@ -182,12 +235,27 @@ __device__ __forceinline__ void reduce_publish(double (&v)[NV], const PdeArgs& a
   __syncthreads();
 }
 
+// An owned value that neighbour rows gather: store it (tagged) in this rank's exchange buffer and, for a
+// boundary row of a multi-GPU partition, straight into the ghost slot of every neighbour rank that needs it.
+template <bool MULTI>
+__device__ __forceinline__ void publish(const PdeArgs& a, int which, int64_t row, double v, u64 tag) {
+  st_tag(a.tb[which] + row, v, tag);
+  if constexpr (MULTI) {
+    for (int e = __ldg(a.send_of_row + row); e >= 0;) {
+      const SendEnt se = a.send_ents[e];
+      st_tag<true>(se.t[which], v, tag);
+      e = se.next;
+    }
+  }
+}
+
 // ---- SELL rows ---------------------------------------------------------------------------------------------
 // acc[m] = sum_k val(m, k) * g(col(k)) over the `width` entries of a row.  Entries are fetched in unrolled
 // batches of kChunk so the index loads, then the gathers, are all in flight together.  TAGGED: the gathered
 // vector is an array of {value, generation} pairs and the gather waits until every element carries `want`.
-template <int NM, bool TAGGED, class ColF, class ValF>
-__device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const void* vec, u64 want, int* fail, double (&acc)[NM]) {
+template <int NM, bool TAGGED, bool SYS, class ColF, class ValF>
+__device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const void* vec, u64 want, int* fail, u64 spin_ns,
+                                         double (&acc)[NM]) {
 #pragma unroll
   for (int m = 0; m < NM; ++m) acc[m] = 0.0;
   for (int k0 = 0; k0 < width; k0 += kChunk) {
@@ -203,14 +271,14 @@ __device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const vo
         g[u] = 0.0;
         if (c[u] >= 0) {
           u64 t;
-          ld_tag(tv + c[u], g[u], t);
+          ld_tag<SYS>(tv + c[u], g[u], t);
           late |= (t != want ? 1u : 0u) << u;
         }
       }
       if (late) {  // some producer is behind: wait for exactly those elements
 #pragma unroll
         for (int u = 0; u < kChunk; ++u)
-          if (late & (1u << u)) g[u] = wait_tag(tv + c[u], want, fail);
+          if (late & (1u << u)) g[u] = wait_tag<SYS>(tv + c[u], want, fail, spin_ns);
       }
     } else {
       const double* dv = static_cast<const double*>(vec);
@@ -240,17 +308,18 @@ struct MatA {
   const PdeArgs& a;
   const double* sa;    // [kChunk][kPdeThreads] A entries of the thread's row (MATSMEM)
   const int32_t* sc;   // [kChunk][kPdeThreads] their columns
-  template <bool TAGGED>
+  // gather of the tagged exchange vector; SYS: ghost columns are written by other GPUs
+  template <bool SYS>
   __device__ __forceinline__ double apply(const RowRef& r, const void* vec, u64 want, int* fail) const {
     double out[1];
     if constexpr (MATSMEM) {
-      sell_row<1, TAGGED>(
+      sell_row<1, true, SYS>(
           r.width, [&](int k) { return sc[k * kPdeThreads + threadIdx.x]; },
-          [&](int, int k) { return sa[k * kPdeThreads + threadIdx.x]; }, vec, want, fail, out);
+          [&](int, int k) { return sa[k * kPdeThreads + threadIdx.x]; }, vec, want, fail, a.spin_ns, out);
     } else {
-      sell_row<1, TAGGED>(
+      sell_row<1, true, SYS>(
           r.width, [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); },
-          [&](int, int k) { return __ldg(a.A + r.beg + (int64_t)k * kSlice + r.lane); }, vec, want, fail, out);
+          [&](int, int k) { return __ldg(a.A + r.beg + (int64_t)k * kSlice + r.lane); }, vec, want, fail, a.spin_ns, out);
     }
     return out[0];
   }
@@ -262,15 +331,15 @@ __device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool 
   auto col = [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); };
   if (x0_prev) {
     double ab[2];
-    sell_row<2, false>(
+    sell_row<2, false, false>(
         r.width, col, [&](int m, int k) { return __ldg((m == 0 ? a.B : a.A) + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0,
-        &dummy, ab);
+        &dummy, 0, ab);
     bi = ab[0];
     ax0 = ab[1];
   } else {
     double b1[1];
-    sell_row<1, false>(
-        r.width, col, [&](int, int k) { return __ldg(a.B + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0, &dummy, b1);
+    sell_row<1, false, false>(
+        r.width, col, [&](int, int k) { return __ldg(a.B + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0, &dummy, 0, b1);
     bi = b1[0];
     ax0 = 0.0;
   }
@@ -357,32 +426,39 @@ __device__ __forceinline__ bool load_row(const PdeArgs& a, RowRef& r, int64_t s,
   }                  \
   }
 
-// Reducer CTA of the pipelined solver: follows the workers' sequence of reductions and decides convergence
-// exactly as they do (same totals, same arithmetic), then reports the result.
-__device__ void pipecg_reducer(const PdeArgs& a, Scratch& sh) {
-  u64 gen = a.gen0;
+// Reducer CTA: follows the workers' sequence of reductions and decides convergence exactly as they do (same
+// totals, same arithmetic), then reports the result and advances the device-resident generation counter.
+__device__ __forceinline__ void finish_reducer(const PdeArgs& a, Scratch& sh, u64 gen, int its, int reason, double rnorm) {
+  write_result(a, its, reason, rnorm);
+  if (threadIdx.x == 0) {
+    a.gen_state[0] = gen;  // every CTA read the old value before its first post, i.e. long before this point
+    if (sh.fail) a.res->error = 1;
+  }
+}
+
+template <bool MULTI>
+__device__ void pipecg_reducer(const PdeArgs& a, Scratch& sh, u64 gen) {
   double bn[1];
-  reduce_publish<1>(bn, a, gen++, sh);
+  reduce_publish<1, MULTI>(bn, a, gen++, sh);
   const double ttol = fmax(a.rtol * sqrt(fabs(bn[0])), a.atol);
   int its = 0, reason = 0;
   double rnorm = 0.0;
   while (true) {
     double acc[3];
-    reduce_publish<3>(acc, a, gen++, sh);
+    reduce_publish<3, MULTI>(acc, a, gen++, sh);
     rnorm = sqrt(fabs(acc[2]));
     reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(acc[0] == acc[0]) || !(acc[1] == acc[1]));
     if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
     if (reason != 0) break;
     ++its;
   }
-  write_result(a, its, reason, rnorm);
-  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+  finish_reducer(a, sh, gen, its, reason, rnorm);
 }
 
-__device__ void cg_reducer(const PdeArgs& a, Scratch& sh) {
-  u64 gen = a.gen0;
+template <bool MULTI>
+__device__ void cg_reducer(const PdeArgs& a, Scratch& sh, u64 gen) {
   double acc3[3];
-  reduce_publish<3>(acc3, a, gen++, sh);
+  reduce_publish<3, MULTI>(acc3, a, gen++, sh);
   double rnorm = sqrt(fabs(acc3[1]));
   const double ttol = fmax(a.rtol * sqrt(fabs(acc3[2])), a.atol);
   int its = 0;
@@ -390,15 +466,14 @@ __device__ void cg_reducer(const PdeArgs& a, Scratch& sh) {
   if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
   while (reason == 0) {
     double pq[1], acc2[2];
-    reduce_publish<1>(pq, a, gen++, sh);
-    reduce_publish<2>(acc2, a, gen++, sh);
+    reduce_publish<1, MULTI>(pq, a, gen++, sh);
+    reduce_publish<2, MULTI>(acc2, a, gen++, sh);
     ++its;
     rnorm = sqrt(fabs(acc2[1]));
     reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(pq[0] == pq[0]) || pq[0] == 0.0);
     if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
   }
-  write_result(a, its, reason, rnorm);
-  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+  finish_reducer(a, sh, gen, its, reason, rnorm);
 }
 
 // The A entries of the thread's single row -> shared memory (MATSMEM), once per launch.
@@ -419,24 +494,55 @@ __device__ __forceinline__ int stage_matrix(const PdeArgs& a, double* sa, int32_
   return width;
 }
 
+// End of a solve: owned x -> global memory (resident mode keeps it in shared memory until here) and the ghost
+// refresh the reference does with state.x.scatter_forward() (base_model.py:242).  MULTI: boundary values go
+// straight into the neighbours' landing zones tagged with this launch's final generation, and this rank's
+// ghosts are copied out of its own landing zone as they arrive - the next kernel of this rank (the cell-model
+// update, which runs on ghosts too) starts only after every neighbour has finished reading this rank's
+// exchange buffers, which is what makes their reuse by the next launch safe.
+#define FINISH_SOLVE(XTAG)                                                                                   \
+  {                                                                                                          \
+    const u64 xtag__ = (XTAG);                                                                               \
+    OWN_ROWS_BEGIN                                                                                           \
+      if (r.row < a.n_owned) {                                                                               \
+        const double xi = V.ld(VX, r);                                                                       \
+        if constexpr (RESIDENT) a.x[r.row] = xi;                                                             \
+        if constexpr (MULTI) {                                                                               \
+          for (int e = __ldg(a.send_of_row + r.row); e >= 0;) {                                              \
+            const SendEnt se = a.send_ents[e];                                                               \
+            st_tag<true>(se.xg, xi, xtag__);                                                                 \
+            e = se.next;                                                                                     \
+          }                                                                                                  \
+        }                                                                                                    \
+      }                                                                                                      \
+    OWN_ROWS_END                                                                                             \
+    if constexpr (MULTI) {                                                                                   \
+      const int64_t n_ghost__ = a.n_local - a.n_owned;                                                       \
+      for (int64_t g = (int64_t)blockIdx.x * kPdeThreads + threadIdx.x; g < n_ghost__;                       \
+           g += (int64_t)a.n_workers * kPdeThreads)                                                          \
+        a.x[a.n_owned + g] = wait_tag<true>(a.xg + g, xtag__, &sh.fail, a.spin_ns);                          \
+    }                                                                                                        \
+    if (sh.fail && threadIdx.x == 0) a.res->error = 1;                                                       \
+  }
+
 // ---- KSPCG (PETSc semantics): two reductions per iteration ------------------------------------------------
 //   q = A p ; alpha = (r,z)/(p,q) ; x += alpha p ; r -= alpha q ; z = M^-1 r ; beta = (r,z)_new/(r,z) ; p = z + beta p
-template <bool RESIDENT, bool MATSMEM>
+template <bool RESIDENT, bool MATSMEM, bool MULTI>
 __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a) {
   extern __shared__ double dyn_smem[];
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
   __syncthreads();
+  u64 gen = a.gen_state[0];  // reduction generations (the same sequence in every CTA and on every rank)
+  u64 vtag = gen;            // generation of the exchanged vector p: <= gen at all times, unique per write
   if (blockIdx.x == a.n_workers) {
-    cg_reducer(a, sh);
+    cg_reducer<MULTI>(a, sh, gen);
     return;
   }
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)a.n_workers * kWarpsPerBlock;
   const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
-  u64 gen = a.gen0;   // reduction generations
-  u64 vtag = a.gen0;  // generation of the exchanged vector p
   const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
   double* sa = dyn_smem + (size_t)NVEC * V.cap;
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
@@ -445,6 +551,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
 
   // ---- K2 + initial residual: r = b - A x0, z = D^-1 r, p = z ---------------------------------------------
   double acc3[3] = {0.0, 0.0, 0.0};  // r.z, norm^2 of r, norm^2 of b (chosen norm)
+  int cur = 0;
   OWN_ROWS_BEGIN
     RowRef g = r;
     if constexpr (MATSMEM) {
@@ -460,7 +567,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
       V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
       V.st(VR, r, ri);
       V.st(VP, r, zi);
-      st_tag(a.t0 + r.row, zi, vtag);
+      publish<MULTI>(a, cur, r.row, zi, vtag);
       acc3[0] = fma(ri, zi, acc3[0]);
       acc3[1] += norm_term(a.norm_type, ri, zi);
       acc3[2] += norm_term(a.norm_type, bi, di * bi);
@@ -474,13 +581,11 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   int its = 0;
   int reason = classify(rnorm, ttol, a.atol, 0, a.max_it, false);
   if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
-  SyncRec* p_cur = a.t0;
-  SyncRec* p_nxt = a.t1;
   while (reason == 0) {
     // ---- K4a: q = A p (gathers wait on the tag of each element), p.q ----------------------------------------
     double pq[1] = {0.0};
     OWN_ROWS_BEGIN
-      const double qi = Aop.template apply<true>(r, p_cur, vtag, &sh.fail);
+      const double qi = Aop.template apply<MULTI>(r, a.tb[cur], vtag, &sh.fail);
       if (r.row < a.n_owned) {
         V.st(VQ, r, qi);
         pq[0] = fma(V.ld(VP, r), qi, pq[0]);
@@ -512,23 +617,16 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     if (reason != 0) break;
     // ---- p = z + beta p (own rows), published with the next generation tag ------------------------------------
     ++vtag;
+    cur ^= 1;
     OWN_ROWS_BEGIN
       if (r.row < a.n_owned) {
         const double pi = fma(beta, V.ld(VP, r), V.ld(VD, r) * V.ld(VR, r));
         V.st(VP, r, pi);
-        st_tag(p_nxt + r.row, pi, vtag);
+        publish<MULTI>(a, cur, r.row, pi, vtag);
       }
     OWN_ROWS_END
-    SyncRec* t = p_cur;
-    p_cur = p_nxt;
-    p_nxt = t;
   }
-  if constexpr (RESIDENT) {
-    OWN_ROWS_BEGIN
-      if (r.row < a.n_owned) a.x[r.row] = V.ld(VX, r);
-    OWN_ROWS_END
-  }
-  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+  FINISH_SOLVE(gen)
 }
 
 // ---- KSPPIPECG: one reduction per iteration, overlapped with the SpMV -----------------------------------------
@@ -539,22 +637,22 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
 //   p = u + beta p ; x += alpha p ; r -= alpha s ; u -= alpha q ; w -= alpha z
 // Only m (and u once, at start-up) is gathered by neighbour rows.  The partial sums of gamma, delta are
 // posted BEFORE n = A m is computed and the totals are awaited after it.
-template <bool RESIDENT, bool MATSMEM>
+template <bool RESIDENT, bool MATSMEM, bool MULTI>
 __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArgs a) {
   extern __shared__ double dyn_smem[];
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
   __syncthreads();
+  u64 gen = a.gen_state[0];
+  u64 vtag = gen;
   if (blockIdx.x == a.n_workers) {
-    pipecg_reducer(a, sh);
+    pipecg_reducer<MULTI>(a, sh, gen);
     return;
   }
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)a.n_workers * kWarpsPerBlock;
   const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
-  u64 gen = a.gen0;
-  u64 vtag = a.gen0;
   const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
   double* sa = dyn_smem + (size_t)NVEC * V.cap;
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
@@ -563,7 +661,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
   int nstamp = 0;
   stamp(a, nstamp);
 
-  // ---- P0: b = B v_ (+ stimulus) ; r = b - A x0 ; u = D^-1 r -> t1 (tag vtag) --------------------------------
+  // ---- P0: b = B v_ (+ stimulus) ; r = b - A x0 ; u = D^-1 r -> buffer 1 (tag vtag) ---------------------------
   double bn[1] = {0.0};
   OWN_ROWS_BEGIN
     RowRef g = r;
@@ -580,21 +678,21 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
       V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
       V.st(VR, r, ri);
       V.st(VU, r, ui);
-      st_tag(a.t1 + r.row, ui, vtag);
+      publish<MULTI>(a, 1, r.row, ui, vtag);
       bn[0] += norm_term(a.norm_type, bi, di * bi);
     }
   OWN_ROWS_END
   post<1>(bn, a, gen, sh);
   stamp(a, nstamp);
 
-  // ---- P1: w = A u ; m = D^-1 w -> t0 (tag vtag+1) ; gamma, delta, norm (overlaps the reduction of |b|) ----------
+  // ---- P1: w = A u ; m = D^-1 w -> buffer 0 (tag vtag+1) ; gamma, delta, norm (overlaps the reduction of |b|) ----
   double acc[3] = {0.0, 0.0, 0.0};
   OWN_ROWS_BEGIN
-    const double wi = Aop.template apply<true>(r, a.t1, vtag, &sh.fail);
+    const double wi = Aop.template apply<MULTI>(r, a.tb[1], vtag, &sh.fail);
     if (r.row < a.n_owned) {
       const double ri = V.ld(VR, r), ui = V.ld(VU, r);
       V.st(VW, r, wi);
-      st_tag(a.t0 + r.row, V.ld(VD, r) * wi, vtag + 1);
+      publish<MULTI>(a, 0, r.row, V.ld(VD, r) * wi, vtag + 1);
       acc[0] = fma(ri, ui, acc[0]);
       acc[1] = fma(wi, ui, acc[1]);
       acc[2] += norm_term(a.norm_type, ri, ui);
@@ -608,14 +706,13 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
 
   int its = 0, reason = 0;
   double rnorm = 0.0, gamma_old = 1.0, alpha_old = 1.0;
-  SyncRec* m_cur = a.t0;
-  SyncRec* m_nxt = a.t1;
+  int cur = 0;  // buffer that holds m
   while (true) {
     post<3>(acc, a, gen, sh);
     stamp(a, nstamp);
     // n = A m while the reduction is in flight
     OWN_ROWS_BEGIN
-      const double ni = Aop.template apply<true>(r, m_cur, vtag, &sh.fail);
+      const double ni = Aop.template apply<MULTI>(r, a.tb[cur], vtag, &sh.fail);
       if (r.row < a.n_owned) V.st(VN, r, ni);
     OWN_ROWS_END
     stamp(a, nstamp);
@@ -654,26 +751,19 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
         V.st(VR, r, ri);
         V.st(VU, r, ui);
         V.st(VW, r, wi);
-        st_tag(m_nxt + r.row, di * wi, vtag + 1);
+        publish<MULTI>(a, cur ^ 1, r.row, di * wi, vtag + 1);
         acc[0] = fma(ri, ui, acc[0]);
         acc[1] = fma(wi, ui, acc[1]);
         acc[2] += norm_term(a.norm_type, ri, ui);
       }
     OWN_ROWS_END
     ++vtag;
-    SyncRec* t = m_cur;
-    m_cur = m_nxt;
-    m_nxt = t;
+    cur ^= 1;
     gamma_old = gamma;
     alpha_old = alpha;
     ++its;
   }
-  if constexpr (RESIDENT) {
-    OWN_ROWS_BEGIN
-      if (r.row < a.n_owned) a.x[r.row] = V.ld(VX, r);
-    OWN_ROWS_END
-  }
-  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+  FINISH_SOLVE(gen)
 }
 
 // measurement: `n` back-to-back reductions (cost of one grid-wide reduction of 3 scalars)
@@ -681,11 +771,11 @@ __global__ void __launch_bounds__(kPdeThreads, 1) sync_bench_kernel(const PdeArg
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
   __syncthreads();
-  u64 gen = a.gen0;
+  u64 gen = a.gen_state[0];
   double v[3] = {1.0, 2.0, 3.0};
   for (int i = 0; i < n; ++i) {
     if (blockIdx.x == a.n_workers) {
-      reduce_publish<3>(v, a, gen++, sh);
+      reduce_publish<3, false>(v, a, gen++, sh);
     } else {
       post<3>(v, a, gen, sh);
       wait<3>(v, a, gen++, sh);
@@ -693,6 +783,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) sync_bench_kernel(const PdeArg
     v[0] = v[0] * 1e-3 + 1.0;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = v[0] + sh.fail;
+  if (blockIdx.x == a.n_workers && threadIdx.x == 0) a.gen_state[0] = gen;
 }
 
 // ---- K3: A = C_m*Mass + dt*theta*K ; B = C_m*Mass - dt*(1-theta)*K ; Jacobi diagonal ------------------
@@ -840,37 +931,74 @@ int pde_setup_launch_config(mono_ctx* c) {
   const size_t nrec = (size_t)8 * c->pde_workers + 8;  // partial sums [2][4][workers] + totals [2][4]
   MONO_CUDA(c, cudaMalloc(&c->recs, sizeof(SyncRec) * nrec));
   MONO_CUDA(c, cudaMemsetAsync(c->recs, 0, sizeof(SyncRec) * nrec, c->stream));
-  c->sync_gen = 1;
-  // the exchanged vector: two tagged buffers over owned + ghost dofs (tag 0 = never written)
+  // ONE allocation holds everything another rank may write into (it is exported with CUDA IPC, halo.cu):
+  //   [ t0 | t1 ]  the exchanged vector, two tagged buffers over owned + ghost dofs (tag 0 = never written)
+  //   [ xg ]       landing zone for the neighbours' final x values, one tagged record per ghost
+  //   [ xrecs ]    cross-rank reduction records [2 parities][4 slots][kMaxRanks]
   const int64_t nl = std::max<int64_t>(c->n_local, 32);
-  for (SyncRec** t : {&c->t0, &c->t1}) {
-    if (*t) cudaFree(*t);
-    MONO_CUDA(c, cudaMalloc(t, sizeof(SyncRec) * nl));
-    MONO_CUDA(c, cudaMemsetAsync(*t, 0, sizeof(SyncRec) * nl, c->stream));
+  const int64_t ng = std::max<int64_t>(c->n_ghost, 1);
+  c->exch_off_t1 = nl;
+  c->exch_off_xg = 2 * nl;
+  c->exch_off_xrecs = 2 * nl + ng;
+  c->exch_recs = 2 * nl + ng + 8 * kMaxRanks;
+  if (c->exch) cudaFree(c->exch);
+  MONO_CUDA(c, cudaMalloc(&c->exch, sizeof(SyncRec) * c->exch_recs));
+  MONO_CUDA(c, cudaMemsetAsync(c->exch, 0, sizeof(SyncRec) * c->exch_recs, c->stream));
+  c->t0 = c->exch;
+  c->t1 = c->exch + c->exch_off_t1;
+  c->xg = c->exch + c->exch_off_xg;
+  c->xrecs = c->exch + c->exch_off_xrecs;
+  if (!c->gen_state) {
+    MONO_CUDA(c, cudaMalloc(&c->gen_state, sizeof(unsigned long long) * 4));
+    const unsigned long long init[4] = {1ull, 0ull, 0ull, 0ull};  // generation 0 = "never written"
+    MONO_CUDA(c, cudaMemcpyAsync(c->gen_state, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  if (const char* e = getenv("MONO_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1.0, atof(e));
   // shared-memory residency: the CG vectors of a CTA's rows, and (one row per thread) the A entries too
   const bool force_stream = getenv("MONO_PDE_STREAM") != nullptr;
   c->resident = c->rows_per_thread <= kMaxResidentRows && !force_stream;
   c->matsmem = c->resident && c->rows_per_thread == 1 && c->max_width <= kChunk && getenv("MONO_PDE_NO_MATSMEM") == nullptr;
   c->resident_smem = c->resident ? (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double) : 0;
   if (c->matsmem) c->resident_smem += (size_t)kChunk * kPdeThreads * (sizeof(double) + sizeof(int32_t));
-  if (c->matsmem && !(opt_in_smem(pde_pipecg_kernel<true, true>, c->resident_smem) && opt_in_smem(pde_cg_kernel<true, true>, c->resident_smem))) {
+  if (c->matsmem && !(opt_in_smem(pde_pipecg_kernel<true, true, false>, c->resident_smem) &&
+                      opt_in_smem(pde_cg_kernel<true, true, false>, c->resident_smem) &&
+                      opt_in_smem(pde_pipecg_kernel<true, true, true>, c->resident_smem) &&
+                      opt_in_smem(pde_cg_kernel<true, true, true>, c->resident_smem))) {
     c->matsmem = false;
     c->resident_smem = (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double);
   }
   if (c->resident && !c->matsmem &&
-      !(opt_in_smem(pde_pipecg_kernel<true, false>, c->resident_smem) && opt_in_smem(pde_cg_kernel<true, false>, c->resident_smem))) {
+      !(opt_in_smem(pde_pipecg_kernel<true, false, false>, c->resident_smem) &&
+        opt_in_smem(pde_cg_kernel<true, false, false>, c->resident_smem) &&
+        opt_in_smem(pde_pipecg_kernel<true, false, true>, c->resident_smem) &&
+        opt_in_smem(pde_cg_kernel<true, false, true>, c->resident_smem))) {
     c->resident = false;
     c->resident_smem = 0;
   }
   return MONO_OK;
 }
 
+template <bool MULTI>
 static const void* pde_kernel_for(const mono_ctx* c) {
   const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
-  if (c->matsmem) return pipe ? (const void*)pde_pipecg_kernel<true, true> : (const void*)pde_cg_kernel<true, true>;
-  if (c->resident) return pipe ? (const void*)pde_pipecg_kernel<true, false> : (const void*)pde_cg_kernel<true, false>;
-  return pipe ? (const void*)pde_pipecg_kernel<false, false> : (const void*)pde_cg_kernel<false, false>;
+  if (c->matsmem) return pipe ? (const void*)pde_pipecg_kernel<true, true, MULTI> : (const void*)pde_cg_kernel<true, true, MULTI>;
+  if (c->resident) return pipe ? (const void*)pde_pipecg_kernel<true, false, MULTI> : (const void*)pde_cg_kernel<true, false, MULTI>;
+  return pipe ? (const void*)pde_pipecg_kernel<false, false, MULTI> : (const void*)pde_cg_kernel<false, false, MULTI>;
+}
+
+static void fill_sync_args(const mono_ctx* c, PdeArgs& a) {
+  a.recs = c->recs;
+  a.gen_state = c->gen_state;
+  a.spin_ns = (u64)(c->spin_timeout_ms * 1e6);
+  a.n_workers = c->pde_workers;
+  a.nranks = c->nranks;
+  a.rank = c->rank;
+  a.xg = c->xg;
+  for (int q = 0; q < kMaxRanks; ++q) a.peer_xrecs[q] = c->peer_xrecs[q];
+  a.peer_xrecs[c->rank] = c->xrecs;
+  a.send_of_row = c->send_of_row_dev;
+  a.send_ents = static_cast<const SendEnt*>(c->send_ents_dev);
 }
 
 static int stim_refresh(mono_ctx* c, double t_eval, int* has_stim) {
@@ -925,25 +1053,26 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   a.v_prev = c->v_prev;
   a.x = c->x;
   for (int k = 0; k < 8; ++k) a.work[k] = c->work[k];
-  a.t0 = c->t0;
-  a.t1 = c->t1;
+  a.tb[0] = c->t0;
+  a.tb[1] = c->t1;
   a.stim_vec = c->stim_vec;
   a.has_stim = has_stim;
   a.rows_per_thread = c->rows_per_thread;
-  a.n_workers = c->pde_workers;
   a.dt = dt;
   a.rtol = c->rtol;
   a.atol = c->atol;
   a.max_it = c->max_it;
   a.norm_type = c->norm_type;
   a.x0_mode = c->x0_mode;
-  a.recs = c->recs;
-  a.gen0 = c->sync_gen;
+  fill_sync_args(c, a);
   a.res = c->ksp_dev;
   a.timeline = c->timeline_dev;
-  c->sync_gen += 3ull * (unsigned long long)std::max(c->max_it, 0) + 16ull;
+  const bool multi = c->nranks > 1;
+  if (multi && !c->peers_ready)
+    return mono_fail(c, MONO_E_INVALID, "multi-rank context: call mono_set_halo (on every rank) before stepping the PDE stage");
   void* args[] = {&a};
-  MONO_CUDA(c, cudaLaunchCooperativeKernel(pde_kernel_for(c), dim3(c->pde_blocks), dim3(c->pde_threads), args, c->resident_smem, c->stream));
+  MONO_CUDA(c, cudaLaunchCooperativeKernel(multi ? pde_kernel_for<true>(c) : pde_kernel_for<false>(c), dim3(c->pde_blocks),
+                                           dim3(c->pde_threads), args, c->resident_smem, c->stream));
   c->launches++;
   return MONO_OK;
 }
@@ -952,10 +1081,7 @@ int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync) {
   if (!c->recs) return mono_fail(c, MONO_E_INVALID, "set matrices first (the synchronisation records belong to the PDE stage)");
   PdeArgs a{};
   a.timeline = nullptr;
-  a.n_workers = c->pde_workers;
-  a.recs = c->recs;
-  a.gen0 = c->sync_gen;
-  c->sync_gen += (unsigned long long)n + 16ull;
+  fill_sync_args(c, a);
   double* out = nullptr;
   MONO_CUDA(c, cudaMalloc(&out, sizeof(double)));
   cudaEvent_t e0, e1;
@@ -973,6 +1099,34 @@ int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync) {
   cudaFree(out);
   c->launches++;
   if (us_per_sync) *us_per_sync = ms * 1e3f / (float)n;
+  return MONO_OK;
+}
+
+// Send table of the in-kernel halo exchange: entry i says that owned row row[i] is a ghost on some neighbour
+// rank whose (peer-mapped) slots in its two exchange buffers and its x landing zone are dst_*[i].
+int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<void*>& dst_t0,
+                         const std::vector<void*>& dst_t1, const std::vector<void*>& dst_xg) {
+  const size_t n = row.size();
+  std::vector<int32_t> first((size_t)std::max<int64_t>(c->n_owned, 1), -1);
+  std::vector<SendEnt> ents(std::max<size_t>(n, 1));
+  for (size_t i = 0; i < n; ++i) {
+    SendEnt& e = ents[i];
+    e.t[0] = static_cast<SyncRec*>(dst_t0[i]);
+    e.t[1] = static_cast<SyncRec*>(dst_t1[i]);
+    e.xg = static_cast<SyncRec*>(dst_xg[i]);
+    e.next = first[row[i]];
+    e.pad = 0;
+    first[row[i]] = (int32_t)i;
+  }
+  if (c->send_of_row_dev) cudaFree(c->send_of_row_dev);
+  if (c->send_ents_dev) cudaFree(c->send_ents_dev);
+  c->send_of_row_dev = nullptr;
+  c->send_ents_dev = nullptr;
+  MONO_CUDA(c, cudaMalloc(&c->send_of_row_dev, sizeof(int32_t) * first.size()));
+  MONO_CUDA(c, cudaMalloc(&c->send_ents_dev, sizeof(SendEnt) * ents.size()));
+  MONO_CUDA(c, cudaMemcpyAsync(c->send_of_row_dev, first.data(), sizeof(int32_t) * first.size(), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaMemcpyAsync(c->send_ents_dev, ents.data(), sizeof(SendEnt) * ents.size(), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   return MONO_OK;
 }
 

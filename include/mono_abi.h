@@ -83,7 +83,8 @@ int mono_host_free(void *ptr);
 
 /* ---- multi-GPU (one rank per GPU; replaces the MPI communicator inside PETSc/dolfinx,
  *      base_model.py:203-206,236,242).  id is the 128-byte NCCL unique id made by rank 0 and
- *      distributed by the caller (bench.py uses torch.distributed).                               */
+ *      distributed by the caller (bench.py uses torch.distributed).  NCCL is loaded with dlopen at this
+ *      point: a libnccl.so.2 already in the process (torch's), else $MONO_NCCL_LIB, else the default path. */
 int mono_comm_unique_id(void *id_out128);
 int mono_comm_init(mono_ctx *ctx, int nranks, int rank, const void *id128);
 /* Halo pattern of this rank's dofs (dolfinx IndexMap: owned dofs first, then ghosts grouped by
@@ -91,6 +92,14 @@ int mono_comm_init(mono_ctx *ctx, int nranks, int rank, const void *id128);
  * the neighbour needs; ghosts [recv_ptr[k], recv_ptr[k+1]) (offsets into the ghost block) come from it. */
 int mono_set_halo(mono_ctx *ctx, int n_nbr, const int32_t *nbr_ranks, const int32_t *send_ptr,
                   const int32_t *send_idx, const int32_t *recv_ptr);
+/* With more than one rank mono_set_halo is COLLECTIVE (every rank calls it, after mono_pde_set_matrices and
+ * mono_comm_init): the ranks exchange CUDA-IPC handles of their exchange buffers so that the persistent PDE
+ * kernel can store boundary values and partial dot products straight into the neighbours' memory over NVLink.
+ * From then on every stepping call (mono_pde_step, mono_split_step, mono_split_solve) must be made by all
+ * ranks in the same order, like the MPI collectives inside the reference's KSP solve.
+ * mono_halo_refresh_nccl: ghost refresh of the PDE solution through ncclSend/ncclRecv - the plain-library
+ * exchange the tests compare the in-kernel one with (state.x.scatter_forward(), base_model.py:242). */
+int mono_halo_refresh_nccl(mono_ctx *ctx);
 
 /* ---- ODE stage: DolfinODESolver / ODESystemSolver (odesolver.py:46-79,135-225) ----------------- */
 /* num_points = owned + ghost dofs (odesolver.py:189-190); v_index = row of the membrane potential. */

@@ -189,7 +189,8 @@ def run_b200(args):
     K, W = args.steps, args.warmup
 
     t_setup = time.perf_counter()
-    solver, info = nied.setup(dx=dx, comm=comm, L=(20.0 * world, 7.0, 3.0), probes=False, ksp_type=args.ksp)
+    solver, info = nied.setup(dx=dx, comm=comm, L=(20.0 * world, 7.0, 3.0), probes=False, ksp_type=args.ksp,
+                              initial_guess_previous=args.x0 == "previous")
     ctx = solver.pde._ctx
     n_global, n_owned = info["n_global"], info["n_owned"]
     setup_s = time.perf_counter() - t_setup
@@ -322,7 +323,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: Niederer slab {20 * world}x7x3 mm, dx={dx} mm, {n_global} nodes "
                                f"({n_owned} owned by rank 0), TP06 GRL1, Godunov split + CN diffusion "
-                               f"(Jacobi-preconditioned {args.ksp}, rtol 1e-5, x0=0), dt={dt} ms", "nodes": n_global,
+                               f"(Jacobi-preconditioned {args.ksp}, rtol 1e-5, x0={'0' if args.x0 == 'zero' else 'v_'}), dt={dt} ms", "nodes": n_global,
                    "l2": "flushed (256 MiB memset) between timed steps; flush outside the CUDA events",
                    "parallelism": f"x-slab partition, {world} rank(s), one per GPU"},
         "warm_l2": {"value": n_global * K / (ms_warm * 1e-3), "ms_per_step": ms_warm / K,
@@ -357,6 +358,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="niederer_dx0.2", choices=sorted(WORKLOADS))
     ap.add_argument("--ksp", default="cg", choices=["cg", "pipecg"], help="Krylov driver of the diffusion solve")
+    ap.add_argument("--x0", default="zero", choices=["zero", "previous"],
+                    help="initial guess of the diffusion solve: zero = PETSc default (as the reference runs), previous = v_")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -360,6 +360,13 @@ class Vector:
     ``.array`` returns the (writable) host array, downloading first if the device copy is newer; because
     the caller may write into it, the next device operation re-uploads it.  ``.array_ro`` gives a
     read-only view without that upload.
+
+    Two refinements keep the per-step host traffic at one copy each way:
+      * uploads from the page-locked mirror are asynchronous; the mirror is not handed out again before the
+        stream has consumed it (``_upload_guard``);
+      * after a fused split step the reference's post-condition v_ode == v == v_ holds on the device, so a
+        vector whose *twin* has already been downloaded refreshes its mirror with a host copy instead of a
+        second device-to-host transfer (``twin_of``).
     """
 
     def __init__(self, n: int):
@@ -368,17 +375,33 @@ class Vector:
         self._host = pinned_zeros(n)
         self._download: Callable[[np.ndarray], None] | None = None
         self._upload: Callable[[np.ndarray], None] | None = None
+        self._sync: Callable[[], None] | None = None
         self.device_newer = False
         self.host_dirty = False
+        self._upload_in_flight = False
+        self._epoch = 0          # bumps whenever the device copy changes
+        self._twin: "Vector | None" = None
+        self._twin_epoch = -1
 
-    def bind(self, download, upload, push_now: bool = True):
-        self._download, self._upload = download, upload
+    def bind(self, download, upload, push_now: bool = True, sync=None):
+        self._download, self._upload, self._sync = download, upload, sync
         self.host_dirty = push_now
         self.device_newer = False
 
+    def _upload_guard(self):
+        if self._upload_in_flight:
+            if self._sync is not None:
+                self._sync()
+            self._upload_in_flight = False
+
     def _pull(self):
+        self._upload_guard()
         if self.device_newer and self._download is not None:
-            self._download(self._host)
+            tw = self._twin
+            if tw is not None and tw._epoch == self._twin_epoch and not tw.device_newer and not tw.host_dirty:
+                np.copyto(self._host, tw._host)  # same device content, already on the host
+            else:
+                self._download(self._host)
             self.device_newer = False
 
     @property
@@ -398,14 +421,20 @@ class Vector:
     def flush_to_device(self):
         if self.host_dirty and self._upload is not None:
             self._upload(self._host)
+            self._upload_in_flight = self._sync is not None
+            self._epoch += 1
+            self._twin = None
         self.host_dirty = False
 
-    def mark_device_newer(self):
+    def mark_device_newer(self, twin_of: "Vector | None" = None):
         self.device_newer = True
         self.host_dirty = False
+        self._epoch += 1
+        self._twin = twin_of
+        self._twin_epoch = twin_of._epoch if twin_of is not None else -1
 
     def scatter_forward(self):
-        """Ghost refresh.  The device step already refreshes ghosts of the solution (halo_refresh)."""
+        """Ghost refresh.  The device step already refreshes ghosts of the solution (inside the PDE kernel)."""
         return None
 
 

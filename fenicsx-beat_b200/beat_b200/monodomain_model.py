@@ -179,8 +179,8 @@ class MonodomainModel:
             self._stim_ids.append(ctx.stim_add(idx, load[idx], t0, t1, amp))
             self._stim_amp.append(amp)
         # host mirrors of the two PDE vectors
-        self._state.x.bind(ctx.get_v, ctx.set_v, push_now=False)
-        self.v_.x.bind(ctx.get_v_prev, ctx.set_v_prev, push_now=False)
+        self._state.x.bind(ctx.get_v, ctx.set_v, push_now=False, sync=ctx.sync)
+        self.v_.x.bind(ctx.get_v_prev, ctx.set_v_prev, push_now=False, sync=ctx.sync)
         self._state._owner = self
         self.ksp = DeviceKSP(ctx)
 

@@ -75,9 +75,11 @@ class MonodomainSplittingSolver:
     def _mark_fused(self) -> None:
         pde, ode = self.pde, self.ode
         ode._mirror.mark_device_newer()
-        ode.v_ode.x.mark_device_newer()
         pde.state.x.mark_device_newer()
-        pde.v_.x.mark_device_newer()
+        # post-condition of the reference's step (monodomain_solver.py:88-97): v_ode == v == v_ ; whoever is read
+        # second on the host copies from the first instead of crossing PCIe again
+        ode.v_ode.x.mark_device_newer(twin_of=pde.state.x)
+        pde.v_.x.mark_device_newer(twin_of=pde.state.x)
 
     def step(self, interval):  # monodomain_solver.py:53-116
         theta = self.theta

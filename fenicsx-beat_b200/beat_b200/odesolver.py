@@ -101,10 +101,10 @@ class DolfinODESolver(BaseDolfinODESolver):
         ctx.ode_create(fun.model_id, fun.scheme_id, self.num_points, self.v_index, num_states)
         self._mirror = _StateMirror(values, ctx)
         self._mirror.flush()
-        self._params_uploaded: np.ndarray | None = None
+        self._params_uploaded: bytes | None = None
         self._params_dirty = True
         self._sync_parameters()
-        self.v_ode.x.bind(ctx.get_v_ode, ctx.set_v_ode, push_now=False)
+        self.v_ode.x.bind(ctx.get_v_ode, ctx.set_v_ode, push_now=False, sync=ctx.sync)
         self._pde = getattr(v_pde, "_owner", None)
 
     # ---- parameters ------------------------------------------------------------------------------
@@ -128,9 +128,10 @@ class DolfinODESolver(BaseDolfinODESolver):
             raise ValueError("parameters=None: the compiled cell models need their parameter vector")
         p = np.asarray(p, dtype=np.float64)
         if p.ndim == 1:
-            if self._params_dirty or self._params_uploaded is None or not np.array_equal(p, self._params_uploaded):
+            raw = p.tobytes()  # users mutate the shared vector in place (pace_train.py:224): compare, cheaply
+            if self._params_dirty or raw != self._params_uploaded:
                 self._ctx.ode_set_params(p, self.fun.derived(p))
-                self._params_uploaded = p.copy()
+                self._params_uploaded = raw
         elif self._params_dirty:
             if p.shape[1] != self.num_points:
                 raise ValueError(f"per-node parameters must have shape (num_parameters, {self.num_points}); got {p.shape}")

@@ -65,9 +65,21 @@ int canonicalize(mono_ctx* c) {
   return copy3(c, n, c->x, row, c->has_ode ? c->v_ode : nullptr, c->v_prev);
 }
 
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+// Host -> device on the context's stream.  Pageable source: the call returns after the copy (self-contained).
+// Page-locked source (mono_host_alloc): the copy is asynchronous - the caller must not modify the buffer before
+// the next synchronising call on this context (mono_sync, any get/info call).
 int h2d(mono_ctx* c, double* dst, const double* src, int64_t n) {
   MONO_CUDA(c, cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  MONO_CUDA(c, cudaStreamSynchronize(c->stream));  // pageable source: keep the ABI call self-contained
+  if (!is_pinned(src)) MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   return MONO_OK;
 }
 

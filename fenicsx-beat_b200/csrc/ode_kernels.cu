@@ -13,6 +13,7 @@
 // Roofline: fp64 pipe / MUFU bound, not HBM: 304 B of state traffic per TP06 node-step against
 // ~2.9k fp64 instructions (DESIGN.md section "K1").
 #include <cstdio>
+#include <cstdlib>
 
 #include "mono_ctx.h"
 
@@ -111,6 +112,19 @@ __global__ void __launch_bounds__(kOdeThreads) ode_kernel_uniform(const OdeArgs 
   if (i < a.n) ode_node<STEP>(a, prm, i);
 }
 
+// Same kernel compiled for 13 one-warp CTAs per SM (<= 152 registers per thread): 416 nodes per SM in flight instead
+// of 384.  The kernel is latency bound at small N (every thread is one long dependent fp64 chain), so what matters
+// is the number of WAVES: the BASELINE slab has 58 176 nodes = 393 per SM, one wave here and two with the
+// 166-register build above.  ode_launch picks the variant with fewer waves.
+constexpr int kOdeThreadsSmall = 32;
+constexpr int kOdeSmallBlocksPerSm = 13;
+template <class STEP, class UPRM>
+__global__ void __launch_bounds__(kOdeThreadsSmall, kOdeSmallBlocksPerSm)
+    ode_kernel_uniform_small(const OdeArgs a, const __grid_constant__ UPRM prm) {
+  const int64_t i = (int64_t)blockIdx.x * kOdeThreadsSmall + threadIdx.x;
+  if (i < a.n) ode_node<STEP>(a, prm, i);
+}
+
 template <class STEP>
 __global__ void __launch_bounds__(kOdeThreads) ode_kernel_pernode(const OdeArgs a, const double* params, int64_t ldp) {
   const int64_t i = (int64_t)blockIdx.x * kOdeThreads + threadIdx.x;
@@ -118,6 +132,16 @@ __global__ void __launch_bounds__(kOdeThreads) ode_kernel_pernode(const OdeArgs 
     NodeParams prm{params, ldp, i};
     ode_node<STEP>(a, prm, i);
   }
+}
+
+template <class K>
+int blocks_per_sm(K kernel, int threads) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    nb = 1;
+  }
+  return nb > 0 ? nb : 1;
 }
 
 template <class STEP, class META>
@@ -131,7 +155,18 @@ int launch_model(mono_ctx* c, const OdeArgs& a) {
     UPRM prm;
     const int total = META::kNumParams + META::kNumDerived;
     for (int k = 0; k < total; ++k) prm.v[k] = k < (int)c->params_host.size() ? c->params_host[k] : 0.0;
-    ode_kernel_uniform<STEP, UPRM><<<grid, kOdeThreads, 0, c->stream>>>(a, prm);
+    bool small = false;
+    if constexpr (META::kNumStates <= 24) {  // the register cap only pays for models that fit it without heavy spilling
+      static const int occ_big = blocks_per_sm(ode_kernel_uniform<STEP, UPRM>, kOdeThreads);
+      static const int occ_small = blocks_per_sm(ode_kernel_uniform_small<STEP, UPRM>, kOdeThreadsSmall);
+      const int64_t gs = (a.n + kOdeThreadsSmall - 1) / kOdeThreadsSmall;
+      const int64_t waves_big = ((int64_t)grid + (int64_t)c->n_sm * occ_big - 1) / ((int64_t)c->n_sm * occ_big);
+      const int64_t waves_small = (gs + (int64_t)c->n_sm * occ_small - 1) / ((int64_t)c->n_sm * occ_small);
+      small = waves_small < waves_big && waves_small <= 2;
+      if (const char* e = getenv("MONO_ODE_VARIANT")) small = e[0] == 's';
+      if (small) ode_kernel_uniform_small<STEP, UPRM><<<(unsigned)gs, kOdeThreadsSmall, 0, c->stream>>>(a, prm);
+    }
+    if (!small) ode_kernel_uniform<STEP, UPRM><<<grid, kOdeThreads, 0, c->stream>>>(a, prm);
   }
   c->launches++;
   MONO_CUDA(c, cudaGetLastError());

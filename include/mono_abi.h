@@ -77,7 +77,10 @@ int mono_sync(mono_ctx *ctx);
 int mono_device_info(mono_ctx *ctx, int *n_sm, int *cc_major, int *cc_minor, int64_t *mem_bytes);
 
 /* Page-locked host memory for the host mirrors of device vectors (pde.state.x.array & co): transfers
- * from/to it run at full PCIe rate.  Needs a CUDA device (MONO_E_CUDA otherwise). */
+ * from/to it run at full PCIe rate.  Needs a CUDA device (MONO_E_CUDA otherwise).
+ * The vector setters (mono_set_v, mono_set_v_prev, mono_set_v_ode, mono_ode_set_state_row) return after the
+ * copy when the source is pageable; from page-locked memory the copy is ASYNCHRONOUS on the context's stream:
+ * do not modify the buffer before the next synchronising call (mono_sync or any get/info call). */
 int mono_host_alloc(int64_t nbytes, void **out);
 int mono_host_free(void *ptr);
 

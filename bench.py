@@ -46,6 +46,7 @@ WORKLOADS = {
     "niederer_dx0.1": (0.1, 0.01),
     "niederer_dx0.05": (0.05, 0.01),
     "niederer_dx0.5": (0.5, 0.01),
+    "niederer_dx0.025": (0.025, 0.01),   # 27.2 M dofs (BASELINE config 4's "~30M")
 }
 
 

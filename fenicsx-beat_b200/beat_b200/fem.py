@@ -96,7 +96,7 @@ class Mesh:
         pts3[:, : points.shape[1]] = points
         self.geometry = _Geometry(pts3)
         self.gdim = points.shape[1]
-        self.cells = np.ascontiguousarray(cells, dtype=np.int64)  # local vertex ids, (ncell, tdim+1)
+        self._cells = None if cells is None else np.ascontiguousarray(cells, dtype=np.int64)  # local vertex ids, (ncell, tdim+1)
         self.topology = _Topology(tdim, index_map)
         self.index_map = index_map
         self.cell_global = cell_global
@@ -121,6 +121,18 @@ class Mesh:
     @property
     def num_local_vertices(self) -> int:
         return self.geometry.x.shape[0]
+
+    @property
+    def cells(self) -> np.ndarray:
+        return self._cells
+
+    @property
+    def num_cells(self) -> int:
+        return self.cells.shape[0]
+
+    def cells_of(self, ids: np.ndarray) -> np.ndarray:
+        """Local vertex ids of the given cells."""
+        return self.cells[ids]
 
     def boundary_facets(self) -> np.ndarray:
         """Exterior facets of the GLOBAL mesh among the local cells, as sorted local vertex tuples."""
@@ -235,7 +247,138 @@ def create_unit_square(comm: Comm, nx: int, ny: int, cell_type=None) -> Mesh:
     return create_rectangle(comm, [np.array([0.0, 0.0]), np.array([1.0, 1.0])], [nx, ny])
 
 
+_KUHN_PERMS = tuple(itertools.permutations((0, 1, 2)))  # axis order of the three steps from corner 000 to corner 111
+
+
+class BoxMesh(Mesh):
+    """Kuhn-split box (dolfinx.mesh.create_box with tetrahedra, src/beat/geometry.py:133-139), x-slab partition.
+
+    Everything is index arithmetic on the (nx+1, ny+1, nz+1) vertex grid, so a 30M-dof slab needs no cell array:
+    cells are generated on demand (``cells`` materialises all of them, ``cells_of`` only the ones asked for) and the
+    P1 matrices are assembled from the six element matrices of the reference cube (``assemble_p1_box``).
+    Numbering (identical to the generic ``_build_local``): owned vertices sorted by global id, then the ghost
+    planes grouped by owner; cell c = perm * ncube + cube, cubes ordered z, y, x (x fastest, local cube range only).
+    """
+
+    def __init__(self, comm: Comm, p0, p1, n):
+        nx, ny, nz = (int(v) for v in n)
+        self.n = (nx, ny, nz)
+        self.p0, self.p1 = tuple(float(v) for v in p0), tuple(float(v) for v in p1)
+        self.h = tuple((self.p1[k] - self.p0[k]) / m for k, m in enumerate(self.n))
+        starts = _partition_1d(nx + 1, comm.size)
+        self.starts = starts
+        lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
+        self.lo, self.hi = lo, hi
+        self.c0, self.c1 = max(lo - 1, 0), min(hi, nx)  # local cubes: every cube that touches an owned vertex
+        self.nxo = hi - lo
+        plane = (ny + 1) * (nz + 1)
+        self.plane = plane
+        self.has_left, self.has_right = lo > 0, hi < nx + 1
+        n_owned = plane * self.nxo
+        self.sx, self.sy, self.sz = 1, nx + 1, (nx + 1) * (ny + 1)
+
+        kk, jj = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), indexing="ij")
+        pl = (kk * (ny + 1) + jj).ravel().astype(np.int64)  # plane-local index -> (k, j)
+        base = pl * (nx + 1)  # gid of (i=0, j, k)
+        gk, gj, gi = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(lo, hi), indexing="ij")
+        owned_g = ((gk * (ny + 1) + gj) * (nx + 1) + gi).ravel().astype(np.int64)
+        ghosts, owners, nbr, send_lists = [], [], [], []
+        if self.has_left:
+            ghosts.append(base + (lo - 1))
+            owners.append(np.full(plane, comm.rank - 1, dtype=np.int32))
+            nbr.append(comm.rank - 1)
+            send_lists.append((pl * self.nxo + 0).astype(np.int32))               # owned plane i = lo
+        if self.has_right:
+            ghosts.append(base + hi)
+            owners.append(np.full(plane, comm.rank + 1, dtype=np.int32))
+            nbr.append(comm.rank + 1)
+            send_lists.append((pl * self.nxo + (self.nxo - 1)).astype(np.int32))  # owned plane i = hi-1
+        ghosts_g = np.concatenate(ghosts) if ghosts else np.zeros(0, np.int64)
+        gown = np.concatenate(owners) if owners else np.zeros(0, np.int32)
+        l2g = np.concatenate([owned_g, ghosts_g])
+        recv_ptr = np.arange(len(nbr) + 1, dtype=np.int32) * plane
+        send_ptr = np.arange(len(nbr) + 1, dtype=np.int32) * plane
+        send_idx = np.concatenate(send_lists).astype(np.int32) if send_lists else np.zeros(0, np.int32)
+        imap = IndexMap(n_owned, ghosts_g, gown, l2g, (nx + 1) * plane, np.asarray(nbr, dtype=np.int32), send_ptr, send_idx, recv_ptr)
+
+        def on_boundary(x):
+            m = np.zeros(x.shape[1], dtype=bool)
+            for k in range(3):
+                m |= np.all(np.isclose(x[k], self.p0[k]), axis=1) | np.all(np.isclose(x[k], self.p1[k]), axis=1)
+            return m
+
+        super().__init__(comm, self._coords(l2g), None, imap, 3,
+                         info={"kind": "box", "n": self.n, "p0": self.p0, "p1": self.p1, "on_boundary": on_boundary})
+
+    def _coords(self, g):
+        nx, ny, _ = self.n
+        gx = g % (nx + 1)
+        gy = (g // (nx + 1)) % (ny + 1)
+        gz = g // self.sz
+        return np.stack([self.p0[0] + self.h[0] * gx, self.p0[1] + self.h[1] * gy, self.p0[2] + self.h[2] * gz], axis=1)
+
+    # ---- local numbering ------------------------------------------------------------------------------
+    def local_index(self, i, j, k):
+        """Local vertex id of grid point (i, j, k), i in [lo-1, hi] (arrays broadcast)."""
+        pl = k * (self.n[1] + 1) + j
+        n_owned = self.index_map.size_local
+        left = n_owned + pl
+        right = n_owned + (self.plane if self.has_left else 0) + pl
+        owned = pl * self.nxo + (i - self.lo)
+        return np.where(i < self.lo, left, np.where(i >= self.hi, right, owned))
+
+    @property
+    def num_cubes(self) -> int:
+        return (self.c1 - self.c0) * self.n[1] * self.n[2]
+
+    @property
+    def num_cells(self) -> int:
+        return 6 * self.num_cubes
+
+    def _cube_ijk(self, cube):
+        w = self.c1 - self.c0
+        return self.c0 + cube % w, (cube // w) % self.n[1], cube // (w * self.n[1])
+
+    def cells_of(self, ids: np.ndarray) -> np.ndarray:
+        ids = np.asarray(ids, dtype=np.int64)
+        ncube = self.num_cubes
+        perm = ids // ncube
+        i, j, k = self._cube_ijk(ids % ncube)
+        steps = np.asarray(_KUHN_PERMS, dtype=np.int64)[perm]  # (m, 3) axis of step 1, 2, 3
+        out = np.empty((ids.shape[0], 4), dtype=np.int64)
+        off = np.zeros((ids.shape[0], 3), dtype=np.int64)
+        out[:, 0] = self.local_index(i, j, k)
+        rows = np.arange(ids.shape[0])
+        for a in range(3):
+            off[rows, steps[:, a]] += 1
+            out[:, a + 1] = self.local_index(i + off[:, 0], j + off[:, 1], k + off[:, 2])
+        return out
+
+    @property
+    def cells(self) -> np.ndarray:
+        if self._cells is None:
+            self._cells = self.cells_of(np.arange(self.num_cells, dtype=np.int64))
+        return self._cells
+
+    def locate_cells(self, ok: np.ndarray) -> np.ndarray:
+        """Cells whose 4 vertices all satisfy the vertex predicate ``ok`` (n_local bools).  Every Kuhn tet contains
+        the 000 and 111 corners of its cube, so only cubes with both corners marked are expanded."""
+        cube = np.arange(self.num_cubes, dtype=np.int64)
+        i, j, k = self._cube_ijk(cube)
+        cand = cube[ok[self.local_index(i, j, k)] & ok[self.local_index(i + 1, j + 1, k + 1)]]
+        ids = (np.arange(6, dtype=np.int64)[:, None] * self.num_cubes + cand[None, :]).ravel()
+        if ids.size == 0:
+            return ids.astype(np.int32)
+        keep = ok[self.cells_of(ids)].all(axis=1)
+        return np.sort(ids[keep]).astype(np.int32 if self.num_cells < 2**31 else np.int64)
+
+
 def create_box(comm: Comm, points, n, cell_type=None, dtype=np.float64) -> Mesh:
+    return BoxMesh(comm, points[0], points[1], n)
+
+
+def _create_box_generic(comm: Comm, points, n) -> Mesh:
+    """The same mesh through the generic builder (global cell array + np.unique): kept as the cross-check of BoxMesh."""
     p0 = tuple(float(v) for v in points[0])
     p1 = tuple(float(v) for v in points[1])
     nx, ny, nz = (int(v) for v in n)
@@ -244,12 +387,13 @@ def create_box(comm: Comm, points, n, cell_type=None, dtype=np.float64) -> Mesh:
     c0, c1 = max(lo - 1, 0), min(hi, nx)
     iz, iy, ix = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(c0, c1), indexing="ij")
     v0 = ((iz * (ny + 1) + iy) * (nx + 1) + ix).ravel().astype(np.int64)
-    sx, sy, sz = 1, nx + 1, (nx + 1) * (ny + 1)
+    strides = (1, nx + 1, (nx + 1) * (ny + 1))
+    sz = strides[2]
     tets = []
-    for perm in itertools.permutations((sx, sy, sz)):
-        a = v0 + perm[0]
-        b = a + perm[1]
-        tets.append(np.stack([v0, a, b, b + perm[2]], axis=1))
+    for perm in _KUHN_PERMS:
+        a = v0 + strides[perm[0]]
+        b = a + strides[perm[1]]
+        tets.append(np.stack([v0, a, b, b + strides[perm[2]]], axis=1))
     cells = np.concatenate(tets, axis=0)
     h = [(p1[k] - p0[k]) / m for k, m in enumerate((nx, ny, nz))]
 
@@ -272,6 +416,78 @@ def create_box(comm: Comm, points, n, cell_type=None, dtype=np.float64) -> Mesh:
     )
 
 
+def assemble_p1_box(mesh: "BoxMesh", Mv: np.ndarray):
+    """CSR (indptr, indices, mass, stiff) of the owned rows of a BoxMesh for a CONSTANT conductivity tensor, without
+    a cell array: the six Kuhn tets of every cube have the same element matrices, so entry (row, row + offset) is a
+    sum of at most 24 constants, accumulated with 96 slice additions over the owned vertex grid."""
+    nx, ny, nz = mesh.n
+    lo, hi, nxo = mesh.lo, mesh.hi, mesh.nxo
+    h = np.asarray(mesh.h)
+    # element matrices of the 6 tets of the reference cube, and the cube-corner offset of each tet vertex
+    corner = np.zeros((6, 4, 3), dtype=np.int64)
+    for p, perm in enumerate(_KUHN_PERMS):
+        for a in range(3):
+            corner[p, a + 1] = corner[p, a]
+            corner[p, a + 1, perm[a]] += 1
+    vol, g = _simplex_measure_and_gradients(corner * h[None, None, :])
+    if Mv.ndim == 0:
+        Ke = float(Mv) * np.einsum("eai,ebi->eab", g, g)
+    else:
+        Ke = np.einsum("eai,ij,ebj->eab", g, Mv, g)
+    Ke *= vol[:, None, None]
+    Me = vol[:, None, None] * ((1.0 + np.eye(4)) / 20.0)[None]
+    # stencil slots = distinct vertex offsets inside a tet, ordered by global-id distance (= local column order)
+    offs = sorted({tuple(corner[p, b] - corner[p, a]) for p in range(6) for a in range(4) for b in range(4)},
+                  key=lambda d: d[0] + d[1] * (nx + 1) + d[2] * (nx + 1) * (ny + 1))
+    slot = {d: s for s, d in enumerate(offs)}
+    ns = len(offs)
+    shape = (nz + 1, ny + 1, nxo)
+    val_m = np.zeros((ns,) + shape)
+    val_k = np.zeros((ns,) + shape)
+    for p in range(6):
+        for a in range(4):
+            ax, ay, az = corner[p, a]
+            i0, i1 = max(mesh.c0, lo - ax), min(mesh.c1, hi - ax)  # cubes whose vertex a is an owned row
+            if i1 <= i0:
+                continue
+            rs = (slice(az, az + nz), slice(ay, ay + ny), slice(i0 + ax - lo, i1 + ax - lo))
+            for b in range(4):
+                s_ = slot[tuple(corner[p, b] - corner[p, a])]
+                val_m[s_][rs] += Me[p, a, b]
+                val_k[s_][rs] += Ke[p, a, b]
+    # columns: neighbour (i+dx, j+dy, k+dz) exists iff it lies in the global grid
+    kk, jj, ii = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(lo, hi), indexing="ij", sparse=True)
+    n_owned = mesh.index_map.size_local
+    cols = np.empty((n_owned, ns), dtype=np.int32)
+    valid = np.empty((n_owned, ns), dtype=bool)
+    for s_, (dx_, dy_, dz_) in enumerate(offs):
+        i2, j2, k2 = ii + dx_, jj + dy_, kk + dz_
+        ok = (i2 >= 0) & (i2 <= nx) & (j2 >= 0) & (j2 <= ny) & (k2 >= 0) & (k2 <= nz)
+        ok = np.broadcast_to(ok, shape)
+        c = mesh.local_index(np.clip(i2, lo - 1, hi), np.clip(j2, 0, ny), np.clip(k2, 0, nz))
+        cols[:, s_] = np.broadcast_to(c, shape).reshape(-1)
+        valid[:, s_] = ok.reshape(-1)
+    mass = np.ascontiguousarray(val_m.reshape(ns, -1).T)
+    stiff = np.ascontiguousarray(val_k.reshape(ns, -1).T)
+    del val_m, val_k
+    # rows next to a ghost plane: their ghost columns carry the largest local ids, so re-sort those rows only
+    pl = np.arange(mesh.plane, dtype=np.int64) * nxo
+    fix = []
+    if mesh.has_left:
+        fix.append(pl)
+    if mesh.has_right:
+        fix.append(pl + (nxo - 1))
+    if fix:
+        rows = np.unique(np.concatenate(fix))
+        key = np.where(valid[rows], cols[rows].astype(np.int64), np.int64(2**40))
+        order = np.argsort(key, axis=1, kind="stable")
+        for arr in (cols, valid, mass, stiff):
+            arr[rows] = np.take_along_axis(arr[rows], order, axis=1)
+    counts = valid.sum(axis=1)
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return indptr, cols[valid], mass[valid], stiff[valid]
+
+
 # ---------------------------------------------------------------------------- entities and tags
 @dataclass
 class MeshTags:
@@ -289,6 +505,8 @@ def locate_entities(mesh: Mesh, dim: int, marker: Callable[[np.ndarray], np.ndar
     """Entities whose vertices ALL satisfy ``marker(x)`` (x has shape (3, npoints)), dolfinx semantics."""
     ok = np.asarray(marker(mesh.geometry.x.T), dtype=bool)
     if dim == mesh.topology.dim:
+        if isinstance(mesh, BoxMesh):
+            return mesh.locate_cells(ok)
         return np.nonzero(ok[mesh.cells].all(axis=1))[0].astype(np.int32)
     if dim == 0:
         return np.nonzero(ok)[0].astype(np.int32)
@@ -594,12 +812,14 @@ def assemble_p1_local(mesh: Mesh, M) -> tuple[np.ndarray, np.ndarray, np.ndarray
     M: scalar, (d,d) tensor, or per-cell (ncell,d,d) tensor.  Entries are accumulated by sorting the
     (row, col) keys - no dense or scipy intermediate - and both matrices share the sparsity."""
     d = mesh.topology.dim
+    Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
+    if isinstance(mesh, BoxMesh) and Mv.ndim in (0, 2) and not os.environ.get("MONO_GENERIC_ASSEMBLY"):
+        return assemble_p1_box(mesh, Mv)
     cells = mesh.cells
     n_owned = mesh.index_map.size_local
     n_local = mesh.num_local_vertices
     x = mesh.geometry.x[:, :d][cells]
     vol, g = _simplex_measure_and_gradients(x)
-    Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
     if Mv.ndim == 0:
         Ke = float(Mv) * np.einsum("eai,ebi->eab", g, g)
     elif Mv.ndim == 2:
@@ -657,12 +877,12 @@ def load_vector(mesh: Mesh, measure: Measure | None, marker: int | None, g: Call
         marker = measure.marker
     if kind == "dx":
         if marker is None or tags is None:
-            ids = np.arange(mesh.cells.shape[0])
+            ids = np.arange(mesh.num_cells)
         else:
             if tags.dim != d:
                 raise ValueError("dx measure needs cell tags")
             ids = tags.find(marker)
-        ents = mesh.cells[ids]
+        ents = mesh.cells_of(ids)
     else:
         if tags is None or marker is None:
             ents = mesh.boundary_facets()

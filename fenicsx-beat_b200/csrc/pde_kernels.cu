@@ -257,7 +257,7 @@ __device__ __forceinline__ void publish(const PdeArgs& a, int which, int64_t row
 // acc[m] = sum_k val(m, k) * g(col(k)) over the `width` entries of a row.  Entries are fetched in unrolled
 // batches of kChunk so the index loads, then the gathers, are all in flight together.  TAGGED: the gathered
 // vector is an array of {value, generation} pairs and the gather waits until every element carries `want`.
-template <int NM, bool TAGGED, bool SYS, class ColF, class ValF>
+template <int NM, bool TAGGED, bool SYS, bool EARLY_A, class ColF, class ValF>
 __device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const void* vec, u64 want, int* fail, u64 spin_ns,
                                          double (&acc)[NM]) {
 #pragma unroll
@@ -267,6 +267,15 @@ __device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const vo
     double g[kChunk];
 #pragma unroll
     for (int u = 0; u < kChunk; ++u) c[u] = (k0 + u < width) ? col(k0 + u) : -1;
+    // the matrix entries of the first operand are requested BEFORE the gathers: they do not depend on the column
+    // indices, and the tagged loads below are `asm volatile`, which the compiler will not move other loads across -
+    // issued after them they would cost a third dependent memory round trip per batch
+    // (EARLY_A is off when the entries sit in shared memory: nothing to hide there, and 32 registers saved)
+    double av0[kChunk];
+    if constexpr (EARLY_A) {
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u) av0[u] = (k0 + u < width) ? val(0, k0 + u) : 0.0;
+    }
     if constexpr (TAGGED) {
       const SyncRec* tv = static_cast<const SyncRec*>(vec);
       unsigned late = 0;
@@ -289,8 +298,14 @@ __device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const vo
 #pragma unroll
       for (int u = 0; u < kChunk; ++u) g[u] = c[u] >= 0 ? __ldg(dv + c[u]) : 0.0;
     }
+    if constexpr (!EARLY_A) {
 #pragma unroll
-    for (int m = 0; m < NM; ++m) {
+      for (int u = 0; u < kChunk; ++u) av0[u] = (k0 + u < width) ? val(0, k0 + u) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) acc[0] = fma(av0[u], g[u], acc[0]);
+#pragma unroll
+    for (int m = 1; m < NM; ++m) {
       double av[kChunk];
 #pragma unroll
       for (int u = 0; u < kChunk; ++u) av[u] = (k0 + u < width) ? val(m, k0 + u) : 0.0;
@@ -317,11 +332,11 @@ struct MatA {
   __device__ __forceinline__ double apply(const RowRef& r, const void* vec, u64 want, int* fail) const {
     double out[1];
     if constexpr (MATSMEM) {
-      sell_row<1, true, SYS>(
+      sell_row<1, true, SYS, false>(
           r.width, [&](int k) { return sc[k * kPdeThreads + threadIdx.x]; },
           [&](int, int k) { return sa[k * kPdeThreads + threadIdx.x]; }, vec, want, fail, a.spin_ns, out);
     } else {
-      sell_row<1, true, SYS>(
+      sell_row<1, true, SYS, true>(
           r.width, [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); },
           [&](int, int k) { return __ldg(a.A + r.beg + (int64_t)k * kSlice + r.lane); }, vec, want, fail, a.spin_ns, out);
     }
@@ -335,14 +350,14 @@ __device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool 
   auto col = [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); };
   if (x0_prev) {
     double ab[2];
-    sell_row<2, false, false>(
+    sell_row<2, false, false, true>(
         r.width, col, [&](int m, int k) { return __ldg((m == 0 ? a.B : a.A) + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0,
         &dummy, 0, ab);
     bi = ab[0];
     ax0 = ab[1];
   } else {
     double b1[1];
-    sell_row<1, false, false>(
+    sell_row<1, false, false, true>(
         r.width, col, [&](int, int k) { return __ldg(a.B + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0, &dummy, 0, b1);
     bi = b1[0];
     ax0 = 0.0;
@@ -428,6 +443,26 @@ __device__ __forceinline__ bool load_row(const PdeArgs& a, RowRef& r, int64_t s,
       load_row<MATSMEM>(a, r, s__, lane, slot__, width_cached);
 #define OWN_ROWS_END \
   }                  \
+  }
+
+// Two rows of the thread per trip (pure vector phases): with the vectors in global memory (streaming mode) the
+// loads of both rows are in flight together - one row at a time leaves an SM with ~20 KB outstanding, too little
+// to cover HBM latency at full bandwidth.  Rows are still visited in the same order (bit-identical sums).
+#define OWN_ROW_PAIRS_BEGIN                                                                                         \
+  {                                                                                                                 \
+    int slot__ = threadIdx.x;                                                                                       \
+    for (int64_t s__ = warp_global; s__ < a.n_slices; s__ += 2 * warp_stride, slot__ += 2 * kPdeThreads) {          \
+      RowRef r0, r1;                                                                                                \
+      r0.row = s__ * kSlice + lane;                                                                                 \
+      r0.lane = lane;                                                                                               \
+      r0.slot = slot__;                                                                                             \
+      r1 = r0;                                                                                                      \
+      r1.row = (s__ + warp_stride) * kSlice + lane;                                                                 \
+      r1.slot = slot__ + kPdeThreads;                                                                               \
+      const bool on0 = r0.row < a.n_owned;                                                                          \
+      const bool on1 = s__ + warp_stride < a.n_slices && r1.row < a.n_owned;
+#define OWN_ROW_PAIRS_END \
+  }                       \
   }
 
 // Reducer CTA: follows the workers' sequence of reductions and decides convergence exactly as they do (same
@@ -552,6 +587,8 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
   const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
   const MatA<MATSMEM> Aop{a, sa, sc};
+  int nstamp = 0;
+  stamp(a, nstamp);
 
   // ---- K2 + initial residual: r = b - A x0, z = D^-1 r, p = z ---------------------------------------------
   double acc3[3] = {0.0, 0.0, 0.0};  // r.z, norm^2 of r, norm^2 of b (chosen norm)
@@ -577,8 +614,10 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
       acc3[2] += norm_term(a.norm_type, bi, di * bi);
     }
   OWN_ROWS_END
+  stamp(a, nstamp);
   post<3>(acc3, a, gen, sh);
   wait<3>(acc3, a, gen++, sh);
+  stamp(a, nstamp);
   double rz = acc3[0];
   double rnorm = sqrt(fabs(acc3[1]));
   const double ttol = fmax(a.rtol * sqrt(fabs(acc3[2])), a.atol);
@@ -595,23 +634,36 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
         pq[0] = fma(V.ld(VP, r), qi, pq[0]);
       }
     OWN_ROWS_END
+    stamp(a, nstamp);
     post<1>(pq, a, gen, sh);
     wait<1>(pq, a, gen++, sh);
+    stamp(a, nstamp);
     const double alpha = rz / pq[0];
     // ---- K4b: x += alpha p ; r -= alpha q ; z = D^-1 r ; r.z and the residual norm (own rows) ------------------
     double acc2[2] = {0.0, 0.0};
-    OWN_ROWS_BEGIN
-      if (r.row < a.n_owned) {
-        const double ri = fma(-alpha, V.ld(VQ, r), V.ld(VR, r));
-        const double zi = V.ld(VD, r) * ri;
-        V.st(VX, r, fma(alpha, V.ld(VP, r), V.ld(VX, r)));
+    {
+      struct In { double q, r, d, p, x; };
+      auto load = [&](const RowRef& r) { return In{V.ld(VQ, r), V.ld(VR, r), V.ld(VD, r), V.ld(VP, r), V.ld(VX, r)}; };
+      auto finish = [&](const RowRef& r, const In& v) {
+        const double ri = fma(-alpha, v.q, v.r);
+        const double zi = v.d * ri;
+        V.st(VX, r, fma(alpha, v.p, v.x));
         V.st(VR, r, ri);
         acc2[0] = fma(ri, zi, acc2[0]);
         acc2[1] += norm_term(a.norm_type, ri, zi);
-      }
-    OWN_ROWS_END
+      };
+      OWN_ROW_PAIRS_BEGIN
+        In v0{}, v1{};
+        if (on0) v0 = load(r0);
+        if (on1) v1 = load(r1);
+        if (on0) finish(r0, v0);
+        if (on1) finish(r1, v1);
+      OWN_ROW_PAIRS_END
+    }
+    stamp(a, nstamp);
     post<2>(acc2, a, gen, sh);
     wait<2>(acc2, a, gen++, sh);
+    stamp(a, nstamp);
     ++its;
     rnorm = sqrt(fabs(acc2[1]));
     const double beta = acc2[0] / rz;
@@ -622,13 +674,23 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     // ---- p = z + beta p (own rows), published with the next generation tag ------------------------------------
     ++vtag;
     cur ^= 1;
-    OWN_ROWS_BEGIN
-      if (r.row < a.n_owned) {
-        const double pi = fma(beta, V.ld(VP, r), V.ld(VD, r) * V.ld(VR, r));
+    {
+      struct In { double p, d, r; };
+      auto load = [&](const RowRef& r) { return In{V.ld(VP, r), V.ld(VD, r), V.ld(VR, r)}; };
+      auto finish = [&](const RowRef& r, const In& v) {
+        const double pi = fma(beta, v.p, v.d * v.r);
         V.st(VP, r, pi);
         publish<MULTI>(a, cur, r.row, pi, vtag);
-      }
-    OWN_ROWS_END
+      };
+      OWN_ROW_PAIRS_BEGIN
+        In v0{}, v1{};
+        if (on0) v0 = load(r0);
+        if (on1) v1 = load(r1);
+        if (on0) finish(r0, v0);
+        if (on1) finish(r1, v1);
+      OWN_ROW_PAIRS_END
+    }
+    stamp(a, nstamp);
   }
   FINISH_SOLVE(gen)
 }

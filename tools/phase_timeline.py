@@ -1,0 +1,30 @@
+"""Per-phase times of one persistent PDE kernel launch (globaltimer stamps of CTA 0)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "fenicsx-beat_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np
+import beat_b200.niederer as nied
+dx = float(sys.argv[1]) if len(sys.argv) > 1 else 0.05
+ksp = sys.argv[2] if len(sys.argv) > 2 else "cg"
+solver, info = nied.setup(dx=dx, probes=False, ksp_type=ksp)
+ctx = solver.pde._ctx
+n = info["n_owned"]
+t, dt = 0.0, 0.01
+for _ in range(10):
+    solver.step((t, t + dt)); t += dt
+ctx.debug_timeline(True, False)
+for rep in range(2):
+    ctx.split_step(t, t + dt, 1.0); t += dt
+    st = np.array(ctx.debug_timeline(True, True), dtype=np.int64)
+    d = np.diff(st) / 1e3
+    print("rows", n, "its", ctx.ksp_info()[0], "total us %.1f" % ((st[-1] - st[0]) / 1e3))
+    if ksp == "cg":
+        names = ["rhs", "red0"] + ["spmv", "red", "axpy", "red", "pupd"] * 20
+        bytes_row = {"rhs": 244, "spmv": 212, "axpy": 56, "pupd": 48}
+    else:
+        names = ["p0", "p1", "red0"] + ["post", "spmv", "wait", "upd"] * 20
+        bytes_row = {"p0": 244, "p1": 220, "spmv": 212, "upd": 152}
+    for nm, us in zip(names, d):
+        gbs = bytes_row.get(nm, 0) * n / (us * 1e-6) / 1e9 if nm in bytes_row else 0
+        print("  %-5s %8.1f us %8.0f GB/s" % (nm, us, gbs))

@@ -193,6 +193,7 @@ def run_b200(args):
     solver, info = nied.setup(dx=dx, comm=comm, L=(20.0 * world, 7.0, 3.0), probes=False, ksp_type=args.ksp,
                               initial_guess_previous=args.x0 == "previous")
     ctx = solver.pde._ctx
+    args.ksp = solver.pde.ksp_type_used
     n_global, n_owned = info["n_global"], info["n_owned"]
     setup_s = time.perf_counter() - t_setup
 
@@ -358,7 +359,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="niederer_dx0.2", choices=sorted(WORKLOADS))
-    ap.add_argument("--ksp", default="cg", choices=["cg", "pipecg"], help="Krylov driver of the diffusion solve")
+    ap.add_argument("--ksp", default="auto", choices=["auto", "cg", "pipecg"],
+                    help="Krylov driver of the diffusion solve (PETSc names; auto = pipecg while the CG vectors fit in shared "
+                         "memory, cg beyond - same iterates in exact arithmetic)")
     ap.add_argument("--x0", default="zero", choices=["zero", "previous"],
                     help="initial guess of the diffusion solve: zero = PETSc default (as the reference runs), previous = v_")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -111,6 +111,7 @@ struct mono_ctx {
   unsigned long long* timeline_dev = nullptr;  // measurement: phase time stamps of the last PDE kernel (64 slots)
   bool matsmem = false;             // ... and so do the A entries (one row per thread)
   bool resident = false;            // the CG vectors of a CTA's rows fit in shared memory
+  bool staged = false;              // streaming mode: SELL slices reach the SpMV through TMA-staged shared memory
   size_t resident_smem = 0;
   KspResult* ksp_dev = nullptr;
   KspResult* ksp_host = nullptr;  // pinned

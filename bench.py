@@ -190,7 +190,8 @@ def run_b200(args):
     K, W = args.steps, args.warmup
 
     t_setup = time.perf_counter()
-    solver, info = nied.setup(dx=dx, comm=comm, L=(20.0 * world, 7.0, 3.0), probes=False, ksp_type=args.ksp,
+    Lx = 20.0 * world if args.scaling == "weak" else 20.0
+    solver, info = nied.setup(dx=dx, comm=comm, L=(Lx, 7.0, 3.0), probes=False, ksp_type=args.ksp,
                               initial_guess_previous=args.x0 == "previous")
     ctx = solver.pde._ctx
     args.ksp = solver.pde.ksp_type_used
@@ -254,6 +255,33 @@ def run_b200(args):
     barrier()
     ms_warm = max_over_ranks(ctx.event_elapsed_ms(2 * K, 2 * K + 1))
 
+    # ---- extra: the same steps with the solve started from v_ instead of zero (not the headline: the reference
+    #      runs PETSc's default zero initial guess; same convergence test, so the answer is at least as accurate) ----
+    fast = None
+    if args.x0 == "zero" and not args.no_extras:
+        rtol_, atol_, max_it_, pc_, norm_, _ = solver.pde._solver_settings()
+        ctx.pde_config(float(solver.pde.C_m), float(solver.pde.parameters["theta"]), rtol_, atol_, max_it_, pc_, norm_, 1)
+        for _ in range(3):
+            ctx.split_step(t, t + dt, 1.0)
+            t += dt
+        itf0, _ = ctx.ksp_totals()
+        barrier()
+        for k in range(K):
+            ctx.l2_flush()
+            ctx.event_record(2 * K + 10 + 2 * k)
+            ctx.split_step(t, t + dt, 1.0)
+            ctx.event_record(2 * K + 11 + 2 * k)
+            t += dt
+        barrier()
+        ms_fast = max_over_ranks(sum(ctx.event_elapsed_ms(2 * K + 10 + 2 * k, 2 * K + 11 + 2 * k) for k in range(K)))
+        itf1, _ = ctx.ksp_totals()
+        fast = {"value": n_global * K / (ms_fast * 1e-3), "ms_per_step": ms_fast / K, "cg_iterations_per_step": (itf1 - itf0) / K,
+                "note": "initial_guess_previous=True (x0 = v_), same rtol/convergence test; L2 flushed between steps"}
+        ctx.pde_config(float(solver.pde.C_m), float(solver.pde.parameters["theta"]), rtol_, atol_, max_it_, pc_, norm_, 0)
+        ctx.split_step(t, t + dt, 1.0)
+        t += dt
+        barrier()
+
     # ---- per-stage device times (separate pass: the stage events add launch gaps) --------------------
     ctx.stage_timing(True)
     ctx.stage_times_ms(reset=True)
@@ -316,20 +344,27 @@ def run_b200(args):
                 "peak": dfma_tflops, "unit": "TFLOP/s (fp64-pipe instructions x2)", "frac": ode_flop / (ode_ms * 1e-3) / 1e12 / dfma_tflops,
                 "traffic": None, "peak_source": "mono_bench_dfma (measured DFMA rate, this run)", "ms_per_launch": ode_ms,
                 "hbm_gbs": ode_bytes / (ode_ms * 1e-3) / 1e9}
+    try:  # DRAM bytes per launch of the same kernels from the committed ncu --set full captures (profiles/)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            tr = json.load(fh).get(f"{args.workload}/{args.ksp}", {}) if world == 1 else {}
+        roof_pde["traffic"], roof_ode["traffic"] = tr.get("pde"), tr.get("ode")
+    except (OSError, ValueError):
+        pass
     dominant = roof_pde if pde_ms >= ode_ms else roof_ode
 
     value = n_global * K / (ms_flushed * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
-        "ms_per_step": ms_flushed / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_flushed / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: Niederer slab {20 * world}x7x3 mm, dx={dx} mm, {n_global} nodes "
+        "config": {"workload": f"{args.workload}: Niederer slab {Lx:g}x7x3 mm, dx={dx} mm, {n_global} nodes "
                                f"({n_owned} owned by rank 0), TP06 GRL1, Godunov split + CN diffusion "
                                f"(Jacobi-preconditioned {args.ksp}, rtol 1e-5, x0={'0' if args.x0 == 'zero' else 'v_'}), dt={dt} ms", "nodes": n_global,
                    "l2": "flushed (256 MiB memset) between timed steps; flush outside the CUDA events",
                    "parallelism": f"x-slab partition, {world} rank(s), one per GPU"},
         "warm_l2": {"value": n_global * K / (ms_warm * 1e-3), "ms_per_step": ms_warm / K,
                     "note": "same K steps back to back, no L2 flush"},
+        "x0_previous": fast,
         "e2e": {"value": n_global * ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * npts,
                 "d2h_bytes_per_step": 8 * npts, "steps": ke, "ms_per_step": e2e_ms / ke,
                 "path": "v_ode.x.array[:]=host_v; ode.from_dolfin(); solver.step((t,t+dt)); host_v[:]=pde.state.x.array"},
@@ -365,6 +400,9 @@ def main():
     ap.add_argument("--x0", default="zero", choices=["zero", "previous"],
                     help="initial guess of the diffusion solve: zero = PETSc default (as the reference runs), previous = v_")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the x0=v_ extra measurement")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = one 20 mm block per GPU (slab grows along x), strong = the 20 mm slab split over the GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

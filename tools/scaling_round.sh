@@ -1,0 +1,25 @@
+#!/bin/bash
+# Scaling pass on an N-GPU box.  usage: bash tools/scaling_round.sh TAG NGPUS
+T=${1:-r01s}; NG=${2:-8}; O=gpurun_out; mkdir -p $O
+run() {  # n, extra bench args..., output name
+  local n=$1; local name=$2; shift 2
+  if [ "$n" = "1" ]; then
+    timeout 600 python bench.py --gpus 1 "$@" > $O/${T}_$name.json 2> $O/${T}_$name.err
+  else
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 400)) \
+      bench.py --gpus $n "$@" > $O/${T}_$name.json 2> $O/${T}_$name.err
+  fi
+  python - <<PY
+import json
+try:
+    d=json.loads(open("$O/${T}_$name.json").read().strip().splitlines()[-1])
+    print("$name", "n=%d"%d["n_gpus"], "%.4g node-steps/s"%d["value"], "%.4f ms/step"%d["ms_per_step"], "warm %.4f"%d["warm_l2"]["ms_per_step"], "e2e %.4g"%d["e2e"]["value"], d["stages"])
+except Exception as e:
+    print("$name ERR", e); print(open("$O/${T}_$name.err").read()[-1500:])
+PY
+}
+nvidia-smi -L | wc -l
+timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q -k "$NG" > $O/${T}_mgpu_pytest.log 2>&1; tail -3 $O/${T}_mgpu_pytest.log
+for n in 1 2 4 8; do [ $n -le $NG ] && run $n weak_dx0.2_n$n --steps 300 --warmup 10 --no-cpu-baseline; done
+for n in 1 2 4 8; do [ $n -le $NG ] && run $n strong_dx0.05_n$n --workload niederer_dx0.05 --scaling strong --steps 30 --warmup 5 --no-cpu-baseline --no-extras; done
+for n in 2 4 8; do [ $n -le $NG ] && run $n strong_dx0.025_n$n --workload niederer_dx0.025 --scaling strong --steps 20 --warmup 5 --no-cpu-baseline --no-extras; done

@@ -23,6 +23,64 @@ from .telemetry import BaseMonitor, NullMonitor
 logger = logging.getLogger(__name__)
 
 
+class ODESystemSolver:
+    """The reference's plain ODE driver (src/beat/odesolver.py:46-79): ``states[:] = fun(states, t0, parameters, dt)`` over
+    an (num_states, num_points) array, here on the device with its own context (no mesh, no PDE).  ``states`` is
+    held by reference like in the reference: it is uploaded before a step when the host copy was handed out since the
+    last one, and read back lazily through the ``states`` property."""
+
+    def __init__(self, fun: DeviceODE, states: np.ndarray, parameters: np.ndarray, missing_variables: np.ndarray | None = None,
+                 monitor: BaseMonitor | None = None, v_index: int = 0, device: int | None = None):
+        import os
+
+        from ._lib import Context
+
+        if not isinstance(fun, DeviceODE):
+            raise TypeError("fun must be a device model handle (beat_b200.models.<model>.<scheme>); there is no CPU fallback")
+        if missing_variables is not None:
+            raise NotImplementedError("missing_variables (mechanics coupling) is outside the monodomain step")
+        states = np.asarray(states, dtype=np.float64)
+        if states.ndim != 2 or states.shape[0] != fun.num_states:
+            raise ValueError(f"states must have shape ({fun.num_states}, num_points); got {states.shape}")
+        self.fun, self.parameters, self.monitor = fun, parameters, monitor or NullMonitor()
+        self.missing_variables = None
+        self._ctx = Context(int(os.environ.get("MONO_DEVICE", "0")) if device is None else device)
+        self._ctx.ode_create(fun.model_id, fun.scheme_id, states.shape[1], int(v_index), fun.num_states)
+        self._mirror = _StateMirror(np.ascontiguousarray(states), self._ctx)
+        self._params_raw: bytes | None = None
+
+    @property
+    def states(self) -> np.ndarray:
+        return self._mirror.get()
+
+    @property
+    def num_points(self) -> int:
+        return self._mirror.host.shape[1]
+
+    @property
+    def num_states(self) -> int:
+        return self._mirror.host.shape[0]
+
+    def _sync_parameters(self) -> None:
+        p = np.asarray(self.parameters, dtype=np.float64)
+        if p.ndim == 1:
+            raw = p.tobytes()
+            if raw != self._params_raw:
+                self._ctx.ode_set_params(p, self.fun.derived(p))
+                self._params_raw = raw
+        else:
+            if p.shape != (self.fun.num_parameters, self.num_points):
+                raise ValueError(f"per-node parameters must have shape ({self.fun.num_parameters}, {self.num_points}); got {p.shape}")
+            self._ctx.ode_set_params(p)  # may have been written by the caller: re-upload (pace_train.py:133-167)
+
+    def step(self, t0: float, dt: float) -> None:  # odesolver.py:67-79
+        with self.monitor.track_time("ode_total_step"):
+            self._mirror.flush()
+            self._sync_parameters()
+            self._ctx.ode_step(t0, dt)
+            self._mirror.mark_device_newer()
+
+
 class BaseDolfinODESolver(abc.ABC):
     v_ode: fem.Function
     v_pde: fem.Function
@@ -92,13 +150,15 @@ class DolfinODESolver(BaseDolfinODESolver):
         self.monitor = monitor or NullMonitor()
 
         # odesolver.py:148-153
-        if np.shape(self.init_states) == self.shape:
+        self._n = int(self.v_ode.x.array_ro.size)  # owned + ghosts, odesolver.py:189-190
+        full = (self.num_states, self._n)
+        if np.shape(self.init_states) == full:
             values = np.array(self.init_states, dtype=np.float64, order="C")
         else:
-            values = np.zeros(self.shape)
+            values = np.zeros(full)
             values.T[:] = self.init_states
         self._ctx = ctx = v_pde.function_space.mesh.device_context()
-        ctx.ode_create(fun.model_id, fun.scheme_id, self.num_points, self.v_index, num_states)
+        ctx.ode_create(fun.model_id, fun.scheme_id, self._n, self.v_index, num_states)
         self._mirror = _StateMirror(values, ctx)
         self._mirror.flush()
         self._params_uploaded: bytes | None = None
@@ -133,8 +193,8 @@ class DolfinODESolver(BaseDolfinODESolver):
                 self._ctx.ode_set_params(p, self.fun.derived(p))
                 self._params_uploaded = raw
         elif self._params_dirty:
-            if p.shape[1] != self.num_points:
-                raise ValueError(f"per-node parameters must have shape (num_parameters, {self.num_points}); got {p.shape}")
+            if p.shape[1] != self._n:
+                raise ValueError(f"per-node parameters must have shape (num_parameters, {self._n}); got {p.shape}")
             self._ctx.ode_set_params(p)
         self._params_dirty = False
 
@@ -208,3 +268,76 @@ class DolfinODESolver(BaseDolfinODESolver):
         functions = [fem.Function(V, name=name) for name in names]
         self.assign_all_states(functions)
         return functions
+
+
+class DolfinMultiODESolver(DolfinODESolver):
+    """Per-region cell models (src/beat/odesolver.py:228-354): ``markers`` is a P1 function holding an integer
+    region id per dof; ``init_states`` / ``parameters`` / ``fun`` / ``num_states`` / ``v_index`` are dicts keyed by it.
+
+    On the device this is ONE kernel launch over all nodes with a per-node parameter table (the reference loops
+    over the regions and runs one NumPy update per region).  That needs the same cell model in every region -
+    the case of the reference's demos (ToR-ORd / TP06 with endo / mid / epi parameter sets); different models per
+    region raise NotImplementedError."""
+
+    def __init__(self, v_ode: fem.Function, v_pde: fem.Function, markers: fem.Function, init_states: dict, parameters: dict,
+                 fun: dict, num_states: dict, v_index: dict, monitor: BaseMonitor | None = None):
+        if v_ode.x.array_ro.size != markers.x.array_ro.size:
+            raise RuntimeError("Marker and voltage need to be in the same function space")  # odesolver.py:241-242
+        self._marker_values = tuple(init_states.keys())
+        funs = [fun[m] for m in self._marker_values]
+        if any(not isinstance(f, DeviceODE) for f in funs):
+            raise TypeError("fun[marker] must be device model handles (there is no CPU fallback)")
+        if len({(f.model_id, f.scheme_id) for f in funs}) != 1 or len({v_index[m] for m in self._marker_values}) != 1:
+            raise NotImplementedError("the device path runs one cell model (and scheme, v_index) over all regions; "
+                                      "regions may differ in parameters and initial states")
+        marr = np.asarray(markers.x.array_ro)
+        self.markers = markers
+        self._inds = {m: marr == m for m in self._marker_values}
+        self._num_points_m = {m: int(w.sum()) for m, w in self._inds.items()}
+        covered = np.zeros(marr.size, dtype=bool)
+        for w in self._inds.values():
+            covered |= w
+        if not covered.all():
+            raise ValueError("every dof needs a marker that has a cell model")
+        f0 = funs[0]
+        ns = f0.num_states
+        n = marr.size
+        values = np.zeros((ns, n))
+        table = np.zeros((f0.num_parameters, n))
+        for m in self._marker_values:
+            if num_states[m] != ns:
+                raise ValueError(f"num_states[{m}] = {num_states[m]} but the model has {ns} states")
+            init = np.asarray(init_states[m], dtype=np.float64)
+            values[:, self._inds[m]] = init if init.shape == (ns, self._num_points_m[m]) else init.reshape(ns, 1)
+            table[:, self._inds[m]] = np.asarray(parameters[m], dtype=np.float64).reshape(-1, 1)
+        self._region_parameters = parameters
+        self._region_raw = {m: np.asarray(parameters[m], dtype=np.float64).tobytes() for m in self._marker_values}
+        super().__init__(v_ode=v_ode, v_pde=v_pde, init_states=values, parameters=table, fun=f0, num_states=ns,
+                         v_index=v_index[self._marker_values[0]], monitor=monitor)
+
+    def _sync_parameters(self) -> None:
+        # the per-region vectors are held by reference and may be mutated in place between steps
+        for m in self._marker_values:
+            raw = np.asarray(self._region_parameters[m], dtype=np.float64).tobytes()
+            if raw != self._region_raw[m]:
+                self._parameters[:, self._inds[m]] = np.asarray(self._region_parameters[m], dtype=np.float64).reshape(-1, 1)
+                self._region_raw[m] = raw
+                self._params_dirty = True
+        super()._sync_parameters()
+
+    # reference surface with a marker argument (odesolver.py:292-303)
+    def values(self, marker: int) -> np.ndarray:  # type: ignore[override]
+        return self._mirror.get()[:, self._inds[marker]]
+
+    def num_parameters(self, marker: int) -> int:  # type: ignore[override]
+        return len(self._region_parameters[marker])
+
+    def shape(self, marker: int):  # type: ignore[override]
+        return (self.num_states, self._num_points_m[marker])
+
+    def num_points(self, marker: int) -> int:  # type: ignore[override]
+        return self._num_points_m[marker]
+
+    @property
+    def full_values(self) -> np.ndarray:
+        return self._mirror.get()

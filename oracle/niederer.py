@@ -46,7 +46,7 @@ def probe_weights(pts, cells, point):
         return np.array([k]), np.array([1.0])
     x = pts[cells]  # (nc, 4, 3)
     T = np.transpose(x[:, 1:, :] - x[:, :1, :], (0, 2, 1))
-    lam = np.linalg.solve(T, np.broadcast_to(p, (x.shape[0], 3)) - x[:, 0, :])
+    lam = np.linalg.solve(T, (np.broadcast_to(p, (x.shape[0], 3)) - x[:, 0, :])[..., None])[..., 0]
     bary = np.concatenate([1.0 - lam.sum(axis=1, keepdims=True), lam], axis=1)
     inside = np.nonzero((bary >= -1e-12).all(axis=1))[0]
     c = int(inside[0])

@@ -164,3 +164,125 @@ def test_niederer_api_matches_oracle_and_probes():
     assert got[info["probe_ids"]["P1"]] == pytest.approx(act["P1"], abs=1e-12)
     assert act["P1"] > 0
     assert np.allclose(solver.pde.probe_values()[info["probe_ids"]["P1"]], v[0])
+
+
+def test_ode_system_solver():
+    """src/beat/odesolver.py:46-79: the plain driver, states held by reference, shared and per-node parameters."""
+    beat = _beat()
+    om = P.oracle_model("tp06")
+    rng = np.random.default_rng(11)
+    n = 777
+    states = P.perturbed_states(om, n, rng, "V")
+    params = beat.models.tp06.init_parameter_values()
+    ode = beat.odesolver.ODESystemSolver(fun=beat.models.tp06.generalized_rush_larsen, states=states.copy(), parameters=params)
+    assert ode.num_points == n and ode.num_states == 19
+    want = states.copy()
+    t = 0.0
+    for _ in range(3):
+        ode.step(t, 0.02)
+        want = om.generalized_rush_larsen(want, t, 0.02, params)
+        t += 0.02
+    assert np.abs(ode.states - want).max() <= 1e-11 * np.abs(want).max()
+    params[beat.models.tp06.parameter_index("g_Na")] *= 0.5  # mutated in place by the user (pace_train.py:224)
+    ode.step(t, 0.02)
+    want = om.generalized_rush_larsen(want, t, 0.02, params)
+    assert np.abs(ode.states - want).max() <= 1e-11 * np.abs(want).max()
+    with pytest.raises(TypeError):
+        beat.odesolver.ODESystemSolver(fun=lambda **kw: None, states=states, parameters=params)
+
+
+def test_dolfin_multi_ode_solver():
+    """src/beat/odesolver.py:228-354: two regions with different parameter sets and initial states."""
+    beat = _beat()
+    fem = beat.fem
+    om = P.oracle_model("tp06")
+    mesh = fem.create_unit_square(fem.COMM_SELF, 6, 6)
+    pde = beat.MonodomainModel(time=fem.Constant(mesh, 0.0), mesh=mesh, M=1.0)
+    V = fem.functionspace(mesh, ("P", 1))
+    markers = fem.Function(V)
+    x = mesh.geometry.x
+    markers.x.array[:] = np.where(x[:, 0] < 0.5, 1, 2)
+    m = beat.models.tp06
+    p = {1: m.init_parameter_values(), 2: m.init_parameter_values(g_Ks=0.098, g_to=0.073)}
+    y = {1: m.init_state_values(), 2: m.init_state_values(V=-80.0)}
+    fun = {k: m.generalized_rush_larsen for k in (1, 2)}
+    ode = beat.odesolver.DolfinMultiODESolver(v_ode=fem.Function(V), v_pde=pde.state, markers=markers, init_states=y, parameters=p,
+                                              fun=fun, num_states={1: 19, 2: 19}, v_index={1: m.state_index("V"), 2: m.state_index("V")})
+    marr = markers.x.array_ro
+    assert ode.num_points(1) == int((marr == 1).sum()) and ode.shape(2) == (19, int((marr == 2).sum()))
+    t = 0.0
+    want = {k: np.repeat(y[k][:, None], ode.num_points(k), axis=1) for k in (1, 2)}
+    for _ in range(4):
+        ode.step(t, 0.05)
+        for k in (1, 2):
+            want[k] = om.generalized_rush_larsen(want[k], t, 0.05, p[k])
+        t += 0.05
+    for k in (1, 2):
+        assert np.abs(ode.values(k) - want[k]).max() <= 1e-11 * np.abs(want[k]).max()
+    ode.to_dolfin()
+    assert np.allclose(ode.v_ode.x.array_ro[marr == 2], want[2][m.state_index("V")])
+    assert ode.full_values.shape == (19, marr.size)
+    with pytest.raises(RuntimeError):
+        bad = fem.Function(fem.functionspace(fem.create_unit_square(fem.COMM_SELF, 3, 3), ("P", 1)))
+        beat.odesolver.DolfinMultiODESolver(v_ode=fem.Function(V), v_pde=pde.state, markers=bad, init_states=y, parameters=p, fun=fun,
+                                            num_states={1: 19, 2: 19}, v_index={1: 0, 2: 0})
+
+
+def test_readme_unit_square_fhn():
+    """BASELINE config 1 (README.md:35-205): unit square 32x32, FitzHugh-Nagumo forward Euler, M = 0.001, dt = 0.01,
+    stimulus 600 on the lower-left quarter for t <= 0.5; 400 steps through the public API against the oracle."""
+    from oracle import fem as ofem
+    from oracle import monodomain as om_mono
+
+    beat = _beat()
+    fem = beat.fem
+    om = P.oracle_model("fhn")
+    N, dt, nsteps = 32, 0.01, 400
+    mesh = fem.create_unit_square(fem.COMM_SELF, N, N)
+    time = fem.Constant(mesh, 0.0)
+    cells = fem.locate_entities(mesh, 2, lambda x: (x[0] <= 0.5 + 1e-12) & (x[1] <= 0.5 + 1e-12))
+    tags = fem.meshtags(mesh, 2, cells, 1)
+    I_s = beat.Stimulus(expr=fem.TimeWindow(time, 0.0, 0.5, 600.0), dZ=fem.Measure("dx", domain=mesh, subdomain_data=tags), marker=1)
+    pde = beat.MonodomainModel(time=time, mesh=mesh, M=0.001, I_s=I_s, dx=I_s.dZ,
+                               params={"petsc_options": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": 1e-12}})
+    m = beat.models.fhn
+    prm = m.init_parameter_values(stim_amplitude=0.0)
+    ode = beat.odesolver.DolfinODESolver(v_ode=fem.Function(pde.V), v_pde=pde.state, fun=m.forward_explicit_euler,
+                                         init_states=m.init_state_values(), parameters=prm, num_states=2, v_index=m.state_index("v"))
+    solver = beat.MonodomainSplittingSolver(pde=pde, ode=ode)
+    solver.solve((0.0, nsteps * dt), dt)
+
+    pts, ocells = ofem.rectangle_mesh(N, N)
+    mass, stiff = ofem.assemble_p1(pts, ocells, 0.001 * np.eye(2))
+    sc = ofem.cells_all_vertices(pts, ocells, lambda x: (x[0] <= 0.5 + 1e-12) & (x[1] <= 0.5 + 1e-12))
+    load = ofem.load_vector_cells(pts, ocells, sc)
+    opde = om_mono.MonodomainModel(mass, stiff, [om_mono.Stimulus.window(load, 0.0, 0.5, 600.0)], C_m=1.0, theta=0.5, solver="lu")
+    oode = om_mono.ODESolver(v_pde=opde.state, init_states=om.init_state_values(), parameters=prm, fun=om.forward_explicit_euler,
+                             num_states=2, v_index=om.state_index("v"))
+    ref = om_mono.SplittingSolver(opde, oode)
+    ref.solve((0.0, nsteps * dt), dt)
+    assert np.allclose(pts, mesh.geometry.x[:, :2])
+    v = solver.pde.state.x.array_ro
+    assert v.max() > opde.state.min() + 10.0  # the stimulus did something
+    assert np.abs(v - opde.state).max() <= 1e-8 * np.abs(opde.state).max()
+    assert np.abs(solver.ode.values - oode.values).max() <= 1e-8 * np.abs(oode.values).max()
+
+
+def test_niederer_full_config_activation_times():
+    """BASELINE config 2 as the demo runs it (dx = 0.2 mm, dt = 0.01 ms, PETSc-default rtol): activation times from the
+    device-side probes agree with the oracle's run of the same algorithm within one dt (north_star) - and, like the
+    oracle, with the published row (demos/niederer_benchmark.py:321) to the oracle's documented tolerance."""
+    from beat_b200 import niederer
+    from oracle import niederer as onied
+
+    dx, dt, T = 0.2, 0.01, 45.0
+    solver, info = niederer.setup(dx=dx, ksp_type="cg")
+    nsteps = int(round(T / dt))
+    solver.solve_on_device(0.0, dt, nsteps)
+    got = solver.pde.activation_times()
+    want = onied.run(dx, dt, T=T, tp06=P.oracle_model("tp06"))
+    pub = dict(zip(onied.POINTS, onied.PUBLISHED[(dx, dt)]))
+    for name, pid in info["probe_ids"].items():
+        assert want[name] >= 0 and got[pid] >= 0, (name, want[name], got[pid])
+        assert abs(got[pid] - want[name]) <= dt + 1e-9, (name, got[pid], want[name])
+        assert abs(got[pid] - pub[name]) <= 0.02 * pub[name] + dt, (name, got[pid], pub[name])

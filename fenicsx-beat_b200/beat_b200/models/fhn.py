@@ -58,7 +58,8 @@ def _derived_grl1(p):
     v__u2 = (p[0] / _ipow(p[5], 2))
     v__u3 = _t0
     v__u4 = abs(v_ds_dt_linearized)
-    return np.array([v_v_th, v_ds_dt_linearized, v__u0, v__u1, v__u2, v__u3, v__u4], dtype=np.float64)
+    v__r0 = (1.0 / v_ds_dt_linearized)
+    return np.array([v_v_th, v_ds_dt_linearized, v__u0, v__u1, v__u2, v__u3, v__u4, v__r0], dtype=np.float64)
 
 
 def _ipow(x, n):
@@ -69,4 +70,4 @@ def _ipow(x, n):
 
 
 forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=2, num_parameters=11, derived=_derived_fe, op_counts={'add': 8, 'mul': 9, 'div': 0, 'exp': 0, 'log': 0, 'sqrt': 0, 'pow': 0, 'floor': 0, 'abs': 0, 'cmp': 3, 'select': 1, 'neg': 2})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=2, num_parameters=11, derived=_derived_grl1, op_counts={'add': 9, 'mul': 11, 'div': 1, 'exp': 1, 'log': 0, 'sqrt': 0, 'pow': 0, 'floor': 0, 'abs': 0, 'cmp': 4, 'select': 2, 'neg': 2})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=2, num_parameters=11, derived=_derived_grl1, op_counts={'add': 9, 'mul': 12, 'div': 0, 'exp': 1, 'log': 0, 'sqrt': 0, 'pow': 0, 'floor': 0, 'abs': 0, 'cmp': 4, 'select': 2, 'neg': 2})

@@ -143,7 +143,29 @@ def _derived_fe(p):
     v__u37 = (_t12 * v_vss)
     v__u38 = (p[31] * v_vmyo)
     v__u39 = (p[31] * v_vss)
-    return np.array([v_Ageo, v_Acap, v_vcell, v_vjsr, v_vmyo, v_vnsr, v_vss, v_Afs, v_PCa, v_PCaK, v_PCap, v_PCaKp, v_constA, v_Io, v_gamma_ko, v_gamma_cao, v_PCaNa, v_PCaNap, v_gamma_nao, v_Gto, v_cmdnmax, v_a2, v_a4, v_b1, v_Pnak, v_k2_i, v_k5_i, v_h10_i, v_h12_i, v_k1_i, v_h11_i, v_k2_ss, v_k5_ss, v_h10_ss, v_h12_ss, v_k1_ss, v_h11_ss, v_Gncx, v_GK1, v_GKb, v_GKr, v_GKs, v_GNaL, v_thLp, v_akik, v_bkik, v_upScale, v_a_rel, v_btp, v_a_relp, v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__u20, v__u21, v__u22, v__u23, v__u24, v__u25, v__u26, v__u27, v__u28, v__u29, v__u30, v__u31, v__u32, v__u33, v__u34, v__u35, v__u36, v__u37, v__u38, v__u39], dtype=np.float64)
+    v__r0 = (1.0 / v__u1)
+    v__r1 = (1.0 / p[69])
+    v__r2 = (1.0 / p[74])
+    v__r3 = (1.0 / p[75])
+    v__r4 = (1.0 / v__u17)
+    v__r5 = (1.0 / p[59])
+    v__r6 = (1.0 / p[57])
+    v__r7 = (1.0 / p[58])
+    v__r8 = (1.0 / p[105])
+    v__r9 = (1.0 / p[108])
+    v__r10 = (1.0 / p[111])
+    v__r11 = (1.0 / p[110])
+    v__r12 = (1.0 / v__u36)
+    v__r13 = (1.0 / v_vmyo)
+    v__r14 = (1.0 / v_vnsr)
+    v__r15 = (1.0 / v__u37)
+    v__r16 = (1.0 / v_vss)
+    v__r17 = (1.0 / v__u38)
+    v__r18 = (1.0 / v__u39)
+    v__r19 = (1.0 / p[12])
+    v__r20 = (1.0 / p[50])
+    v__r21 = (1.0 / v_thLp)
+    return np.array([v_Ageo, v_Acap, v_vcell, v_vjsr, v_vmyo, v_vnsr, v_vss, v_Afs, v_PCa, v_PCaK, v_PCap, v_PCaKp, v_constA, v_Io, v_gamma_ko, v_gamma_cao, v_PCaNa, v_PCaNap, v_gamma_nao, v_Gto, v_cmdnmax, v_a2, v_a4, v_b1, v_Pnak, v_k2_i, v_k5_i, v_h10_i, v_h12_i, v_k1_i, v_h11_i, v_k2_ss, v_k5_ss, v_h10_ss, v_h12_ss, v_k1_ss, v_h11_ss, v_Gncx, v_GK1, v_GKb, v_GKr, v_GKs, v_GNaL, v_thLp, v_akik, v_bkik, v_upScale, v_a_rel, v_btp, v_a_relp, v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__u20, v__u21, v__u22, v__u23, v__u24, v__u25, v__u26, v__u27, v__u28, v__u29, v__u30, v__u31, v__u32, v__u33, v__u34, v__u35, v__u36, v__u37, v__u38, v__u39, v__r0, v__r1, v__r2, v__r3, v__r4, v__r5, v__r6, v__r7, v__r8, v__r9, v__r10, v__r11, v__r12, v__r13, v__r14, v__r15, v__r16, v__r17, v__r18, v__r19, v__r20, v__r21], dtype=np.float64)
 
 
 def _derived_grl1(p):
@@ -255,7 +277,32 @@ def _derived_grl1(p):
     v__u38 = (_t12 * v_vss)
     v__u39 = (p[31] * v_vmyo)
     v__u40 = (p[31] * v_vss)
-    return np.array([v_Ageo, v_Acap, v_vcell, v_vjsr, v_vmyo, v_vnsr, v_vss, v_Afs, v_PCa, v_PCaK, v_PCap, v_PCaKp, v_constA, v_Io, v_gamma_ko, v_gamma_cao, v_PCaNa, v_PCaNap, v_gamma_nao, v_Gto, v_cmdnmax, v_a2, v_a4, v_b1, v_Pnak, v_k2_i, v_k5_i, v_h10_i, v_h12_i, v_k1_i, v_h11_i, v_k2_ss, v_k5_ss, v_h10_ss, v_h12_ss, v_k1_ss, v_h11_ss, v_Gncx, v_GK1, v_GKb, v_GKr, v_GKs, v_GNaL, v_thLp, v_akik, v_bkik, v_upScale, v_a_rel, v_btp, v_a_relp, v_djca_dt_linearized, v_dhL_dt_linearized, v_dhLp_dt_linearized, v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__u20, v__u21, v__u22, v__u23, v__u24, v__u25, v__u26, v__u27, v__u28, v__u29, v__u30, v__u31, v__u32, v__u33, v__u34, v__u35, v__u36, v__u37, v__u38, v__u39, v__u40], dtype=np.float64)
+    v__r0 = (1.0 / v__u1)
+    v__r1 = (1.0 / p[69])
+    v__r2 = (1.0 / p[74])
+    v__r3 = (1.0 / p[75])
+    v__r4 = (1.0 / v__u17)
+    v__r5 = (1.0 / p[59])
+    v__r6 = (1.0 / p[57])
+    v__r7 = (1.0 / p[58])
+    v__r8 = (1.0 / p[105])
+    v__r9 = (1.0 / p[108])
+    v__r10 = (1.0 / p[111])
+    v__r11 = (1.0 / p[110])
+    v__r12 = (1.0 / v__u37)
+    v__r13 = (1.0 / v_vmyo)
+    v__r14 = (1.0 / v_vnsr)
+    v__r15 = (1.0 / v__u38)
+    v__r16 = (1.0 / v_vss)
+    v__r17 = (1.0 / v__u39)
+    v__r18 = (1.0 / v__u40)
+    v__r19 = (1.0 / p[12])
+    v__r20 = (1.0 / p[50])
+    v__r21 = (1.0 / v_thLp)
+    v__r22 = (1.0 / v_djca_dt_linearized)
+    v__r23 = (1.0 / v_dhL_dt_linearized)
+    v__r24 = (1.0 / v_dhLp_dt_linearized)
+    return np.array([v_Ageo, v_Acap, v_vcell, v_vjsr, v_vmyo, v_vnsr, v_vss, v_Afs, v_PCa, v_PCaK, v_PCap, v_PCaKp, v_constA, v_Io, v_gamma_ko, v_gamma_cao, v_PCaNa, v_PCaNap, v_gamma_nao, v_Gto, v_cmdnmax, v_a2, v_a4, v_b1, v_Pnak, v_k2_i, v_k5_i, v_h10_i, v_h12_i, v_k1_i, v_h11_i, v_k2_ss, v_k5_ss, v_h10_ss, v_h12_ss, v_k1_ss, v_h11_ss, v_Gncx, v_GK1, v_GKb, v_GKr, v_GKs, v_GNaL, v_thLp, v_akik, v_bkik, v_upScale, v_a_rel, v_btp, v_a_relp, v_djca_dt_linearized, v_dhL_dt_linearized, v_dhLp_dt_linearized, v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__u20, v__u21, v__u22, v__u23, v__u24, v__u25, v__u26, v__u27, v__u28, v__u29, v__u30, v__u31, v__u32, v__u33, v__u34, v__u35, v__u36, v__u37, v__u38, v__u39, v__u40, v__r0, v__r1, v__r2, v__r3, v__r4, v__r5, v__r6, v__r7, v__r8, v__r9, v__r10, v__r11, v__r12, v__r13, v__r14, v__r15, v__r16, v__r17, v__r18, v__r19, v__r20, v__r21, v__r22, v__r23, v__r24], dtype=np.float64)
 
 
 def _ipow(x, n):
@@ -265,5 +312,5 @@ def _ipow(x, n):
     return r
 
 
-forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=45, num_parameters=112, derived=_derived_fe, op_counts={'add': 404, 'mul': 496, 'div': 228, 'exp': 75, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 0, 'cmp': 9, 'select': 11, 'neg': 77})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=45, num_parameters=112, derived=_derived_grl1, op_counts={'add': 439, 'mul': 538, 'div': 283, 'exp': 109, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 8, 'cmp': 17, 'select': 19, 'neg': 83})
+forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=45, num_parameters=112, derived=_derived_fe, op_counts={'add': 404, 'mul': 576, 'div': 148, 'exp': 75, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 0, 'cmp': 9, 'select': 11, 'neg': 77})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=45, num_parameters=112, derived=_derived_grl1, op_counts={'add': 439, 'mul': 621, 'div': 200, 'exp': 109, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 8, 'cmp': 17, 'select': 19, 'neg': 83})

@@ -63,7 +63,14 @@ def _derived_fe(p):
     v__u17 = ((2.0 * p[41]) * p[45])
     v__u18 = (p[48] + p[50])
     v__u19 = (p[47] * p[45])
-    return np.array([v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19], dtype=np.float64)
+    v__r0 = (1.0 / v__u6)
+    v__r1 = (1.0 / v__u13)
+    v__r2 = (1.0 / p[47])
+    v__r3 = (1.0 / v__u17)
+    v__r4 = (1.0 / p[41])
+    v__r5 = (1.0 / p[49])
+    v__r6 = (1.0 / v__u19)
+    return np.array([v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__r0, v__r1, v__r2, v__r3, v__r4, v__r5, v__r6], dtype=np.float64)
 
 
 def _derived_grl1(p):
@@ -91,7 +98,14 @@ def _derived_grl1(p):
     v__u17 = ((2.0 * p[41]) * p[45])
     v__u18 = (p[48] + p[50])
     v__u19 = (p[47] * p[45])
-    return np.array([v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19], dtype=np.float64)
+    v__r0 = (1.0 / v__u6)
+    v__r1 = (1.0 / v__u13)
+    v__r2 = (1.0 / p[47])
+    v__r3 = (1.0 / v__u17)
+    v__r4 = (1.0 / p[41])
+    v__r5 = (1.0 / p[49])
+    v__r6 = (1.0 / v__u19)
+    return np.array([v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__r0, v__r1, v__r2, v__r3, v__r4, v__r5, v__r6], dtype=np.float64)
 
 
 def _ipow(x, n):
@@ -101,5 +115,5 @@ def _ipow(x, n):
     return r
 
 
-forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=19, num_parameters=53, derived=_derived_fe, op_counts={'add': 177, 'mul': 147, 'div': 120, 'exp': 51, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 0, 'cmp': 4, 'select': 5, 'neg': 11})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=19, num_parameters=53, derived=_derived_grl1, op_counts={'add': 191, 'mul': 161, 'div': 145, 'exp': 64, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 1, 'cmp': 5, 'select': 6, 'neg': 11})
+forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=19, num_parameters=53, derived=_derived_fe, op_counts={'add': 177, 'mul': 195, 'div': 72, 'exp': 51, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 0, 'cmp': 4, 'select': 5, 'neg': 11})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=19, num_parameters=53, derived=_derived_grl1, op_counts={'add': 191, 'mul': 209, 'div': 97, 'exp': 64, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 1, 'cmp': 5, 'select': 6, 'neg': 11})

@@ -47,7 +47,7 @@ class Program:
         return [p for p in self.model.parameters if p in used]
 
 
-def build_program(model: OdeModel, scheme: str) -> Program:
+def build_program(model: OdeModel, scheme: str, reciprocal_constants: bool = True) -> Program:
     if scheme not in SCHEMES:
         raise ValueError(f"unknown scheme {scheme!r}; have {SCHEMES}")
     prog = Program(model=model, scheme=scheme)
@@ -147,7 +147,47 @@ def build_program(model: OdeModel, scheme: str) -> Program:
     memo: dict = {}
     prog.body = [(n, ir.rebuild(e, leaf_map, memo)) for n, e in prog.body]
     prog.outputs = [ir.rebuild(e, leaf_map, memo) for e in prog.outputs]
+    if reciprocal_constants:
+        _divisions_by_constants_to_multiplications(prog, params, uniform_names)
     return prog
+
+
+def _divisions_by_constants_to_multiplications(prog: Program, params: set, uniform_names: set) -> None:
+    """x / c  ->  x * (1/c) when c is a literal or a per-launch constant (a parameter or a hoisted parameter-only
+    value): the reciprocal is folded at generation time (literal) or becomes one more hoisted constant.  A fp64
+    divide is ~8 fp64-pipe instructions on the device (csrc/ode_math.cuh), a multiply one; about a third of the
+    divisions of TP06 / ToR-ORd have such a divisor.  The product differs from the correctly rounded quotient by at
+    most 1 ulp - inside the budget the device division already has, and far inside the 1e-12 parity bar.  DEVICE
+    code only: the oracle keeps true divisions (it is generated independently, oracle/gen_models.py)."""
+    memo: dict = {}
+    rcp_of: dict[str, ir.Node] = {}
+
+    def rec(x: ir.Node) -> ir.Node:
+        r = memo.get(id(x))
+        if r is not None:
+            return r
+        if not x.args:
+            r = x
+        else:
+            a = tuple(rec(c) for c in x.args)
+            r = x if all(p is q for p, q in zip(a, x.args)) else ir._mk(x.kind, a, x.value)
+            if r.kind == "div":
+                top, den = r.args
+                if ir.is_num(den) and den.value != 0.0:
+                    r = ir.mul(top, ir.num(1.0 / den.value))
+                elif den.kind == "sym" and (den.value in params or den.value in uniform_names) and not ir.is_num(top):
+                    h = rcp_of.get(den.value)
+                    if h is None:
+                        name = f"_r{len(rcp_of)}"
+                        prog.uniform.append((name, ir.div(ir.ONE, den)))
+                        uniform_names.add(name)
+                        h = rcp_of[den.value] = ir.sym(name)
+                    r = ir.mul(top, h)
+        memo[id(x)] = r
+        return r
+
+    prog.body = [(n, rec(e)) for n, e in prog.body]
+    prog.outputs = [rec(e) for e in prog.outputs]
 
 
 def op_counts(prog: Program, include_uniform: bool = False) -> dict[str, int]:

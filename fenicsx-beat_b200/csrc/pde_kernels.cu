@@ -621,14 +621,27 @@ __device__ __forceinline__ int stage_matrix(const PdeArgs& a, double* sa, int32_
   if (warp_global < a.n_slices) {
     const int64_t beg = __ldg(a.slice_ptr + warp_global);
     width = (int)((__ldg(a.slice_ptr + warp_global + 1) - beg) / kSlice);
+    // asynchronous copies (LDGSTS): they complete while the RHS phase runs; stage_wait() precedes the first SpMV.
+    // Every thread reads back only what it copied itself, so no barrier is needed.
 #pragma unroll
     for (int k = 0; k < kChunk; ++k) {
-      const bool on = k < width;
-      sc[k * kPdeThreads + threadIdx.x] = on ? __ldg(a.cols + beg + (int64_t)k * kSlice + lane) : -1;
-      sa[k * kPdeThreads + threadIdx.x] = on ? __ldg(a.A + beg + (int64_t)k * kSlice + lane) : 0.0;
+      int32_t* dc = sc + k * kPdeThreads + threadIdx.x;
+      double* da = sa + k * kPdeThreads + threadIdx.x;
+      if (k < width) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dc)), "l"(a.cols + beg + (int64_t)k * kSlice + lane) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(da)), "l"(a.A + beg + (int64_t)k * kSlice + lane) : "memory");
+      } else {
+        *dc = -1;
+        *da = 0.0;
+      }
     }
   }
   return width;
+}
+
+template <bool MATSMEM>
+__device__ __forceinline__ void stage_wait() {
+  if constexpr (MATSMEM) asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // End of a solve: owned x -> global memory (resident mode keeps it in shared memory until here) and the ghost
@@ -765,6 +778,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   int its = 0;
   int reason = classify(rnorm, ttol, a.atol, 0, a.max_it, false);
   if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+  stage_wait<MATSMEM>();
   while (reason == 0) {
     // ---- K4a: q = A p (gathers wait on the tag of each element), p.q ----------------------------------------
     double pq[1] = {0.0};
@@ -914,6 +928,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
   stamp(a, nstamp);
 
   // ---- P1: w = A u ; m = D^-1 w -> buffer 0 (tag vtag+1) ; gamma, delta, norm (overlaps the reduction of |b|) ----
+  stage_wait<MATSMEM>();
   double acc[3] = {0.0, 0.0, 0.0};
   OWN_ROWS_BEGIN
     const double wi = Aop.template apply<MULTI>(r, a.tb[1], vtag, &sh.fail);

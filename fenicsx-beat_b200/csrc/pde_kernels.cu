@@ -199,7 +199,11 @@ __device__ __forceinline__ void post(const double (&v)[NV], const PdeArgs& a, u6
 // (Measured alternatives, both rejected: (a) no reducer, every CTA polls all 3 x 147 partial sums itself - one L2
 // hop fewer on paper, but 147 SMs hammering the same 55 cache lines made the wait 2.2 us instead of 0.3-0.9 us;
 // (b) a private copy of the totals per worker CTA to avoid 147 pollers on one line - the 441 extra stores and the
-// extra barrier in the reducer cost more than the hot line: PDE stage 51 us instead of 45 us.)
+// extra barrier in the reducer cost more than the hot line: PDE stage 51 us instead of 45 us;
+// (c) thread-block clusters: a service warp per CTA, CTA sums handed to the cluster leader through distributed shared
+// memory + mbarriers, leaders all-to-all through tagged global records, totals written back into the members' shared
+// memory - micro-benchmarked at 2.87 us per reduction (8-CTA clusters, 15 leaders) against 2.14 us for this
+// reducer-CTA scheme: the two DSMEM hand-offs are not cheaper than the L2 hop they replace, and the chain is longer.)
 template <int NV>
 __device__ __forceinline__ void wait(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
   if (threadIdx.x < NV) sh.totals[threadIdx.x] = wait_tag(total_recs(a, gen) + threadIdx.x, gen, &sh.fail, a.spin_ns);

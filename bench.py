@@ -192,7 +192,7 @@ def run_b200(args):
     t_setup = time.perf_counter()
     Lx = 20.0 * world if args.scaling == "weak" else 20.0
     solver, info = nied.setup(dx=dx, comm=comm, L=(Lx, 7.0, 3.0), probes=False, ksp_type=args.ksp,
-                              initial_guess_previous=args.x0 == "previous")
+                              initial_guess_previous=args.x0 == "previous", pc_type=None if args.pc == "auto" else args.pc)
     ctx = solver.pde._ctx
     args.ksp = solver.pde.ksp_type_used
     n_global, n_owned = info["n_global"], info["n_owned"]
@@ -359,7 +359,7 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: Niederer slab {Lx:g}x7x3 mm, dx={dx} mm, {n_global} nodes "
                                f"({n_owned} owned by rank 0), TP06 GRL1, Godunov split + CN diffusion "
-                               f"(Jacobi-preconditioned {args.ksp}, rtol 1e-5, x0={'0' if args.x0 == 'zero' else 'v_'}), dt={dt} ms", "nodes": n_global,
+                               f"({solver.pde.pc_type_used}-preconditioned {args.ksp}, rtol 1e-5, x0={'0' if args.x0 == 'zero' else 'v_'}), dt={dt} ms", "nodes": n_global,
                    "l2": "flushed (256 MiB memset) between timed steps; flush outside the CUDA events",
                    "parallelism": f"x-slab partition, {world} rank(s), one per GPU"},
         "warm_l2": {"value": n_global * K / (ms_warm * 1e-3), "ms_per_step": ms_warm / K,
@@ -397,6 +397,8 @@ def main():
     ap.add_argument("--ksp", default="auto", choices=["auto", "cg", "pipecg"],
                     help="Krylov driver of the diffusion solve (PETSc names; auto = pipecg while the CG vectors fit in shared "
                          "memory, cg beyond - same iterates in exact arithmetic)")
+    ap.add_argument("--pc", default="auto", choices=["auto", "jacobi", "chebyshev"],
+                    help="preconditioner (auto: the reference's hypre request mapped to the fastest native one for the mesh size)")
     ap.add_argument("--x0", default="zero", choices=["zero", "previous"],
                     help="initial guess of the diffusion solve: zero = PETSc default (as the reference runs), previous = v_")
     ap.add_argument("--no-cpu-baseline", action="store_true")

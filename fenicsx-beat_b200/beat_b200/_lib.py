@@ -50,6 +50,7 @@ SIGNATURES = {
     "mono_pde_set_matrices": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_int64_p, c_int32_p, c_double_p, c_double_p]),
     "mono_pde_config": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mono_pde_set_ksp_type": (C.c_int, [C.c_void_p, C.c_int]),
+    "mono_pde_set_chebyshev": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "mono_pde_set_dt": (C.c_int, [C.c_void_p, C.c_double]),
     "mono_stim_add": (C.c_int, [C.c_void_p, C.c_int64, c_int32_p, c_double_p, C.c_double, C.c_double, C.c_double]),
     "mono_stim_set_amplitude": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
@@ -314,6 +315,9 @@ class Context:
 
     def pde_config(self, C_m, theta, rtol, atol, max_it, pc_type, norm_type, x0_mode):
         self._ck(self.lib.mono_pde_config(self.h, C_m, theta, rtol, atol, max_it, pc_type, norm_type, x0_mode))
+
+    def pde_set_chebyshev(self, steps: int, kappa: float):
+        self._ck(self.lib.mono_pde_set_chebyshev(self.h, int(steps), float(kappa)))
 
     def pde_set_ksp_type(self, ksp_type: int):
         self._ck(self.lib.mono_pde_set_ksp_type(self.h, ksp_type))

@@ -24,7 +24,7 @@ from .telemetry import BaseMonitor, NullMonitor
 
 logger = logging.getLogger(__name__)
 
-PC = {"none": 0, "jacobi": 1}
+PC = {"none": 0, "jacobi": 1, "chebyshev": 2}
 NORM = {"preconditioned": 0, "unpreconditioned": 1, "natural": 2, "default": 0}
 
 
@@ -73,10 +73,11 @@ class MonodomainModel:
 
     Parameters as in the reference (monodomain_model.py:27-40, base_model.py:73-82).  ``M`` is a float, a
     :class:`fem.Constant`, a (d,d) array or a per-cell (ncell,d,d) array.  Solver selection follows
-    ``params["petsc_options"]``: ksp_type "cg" -> device CG with ksp_rtol / ksp_atol / ksp_max_it /
-    ksp_norm_type; pc_type "jacobi" | "none" are native, "hypre"/"gamg"/... map to Jacobi (the system is
-    mass-dominated); ksp_type "preonly" (the reference's LU/MUMPS default) is
-    reproduced by iterating the same CG to rtol 1e-12.
+    ``params["petsc_options"]``: ksp_type "cg" | "pipecg" | "auto" -> device CG with ksp_rtol / ksp_atol / ksp_max_it /
+    ksp_norm_type; pc_type "jacobi" | "none" | "chebyshev" (Chebyshev polynomial in the Jacobi-scaled operator,
+    pc_chebyshev_steps / pc_chebyshev_kappa, pipecg only) are native; "hypre"/"gamg"/... map to Jacobi, or with
+    ksp_type "auto" to whatever is fastest for the mesh size (the system is mass-dominated, SURVEY.md section 8a);
+    ksp_type "preonly" (the reference's LU/MUMPS default) is reproduced by iterating the same CG to rtol 1e-12.
     """
 
     def __init__(self, time: fem.Constant, mesh: fem.Mesh, M, I_s=None, params: dict | None = None, C_m: float = 1.0,
@@ -138,7 +139,7 @@ class MonodomainModel:
             rtol = float(opts.get("ksp_rtol", 1e-5))  # PETSc defaults
             atol = float(opts.get("ksp_atol", 1e-50))
             max_it = int(opts.get("ksp_max_it", 10000))
-            pc_id = PC["none"] if pc == "none" else PC["jacobi"]
+            pc_id = PC.get(pc, PC["jacobi"])
         else:
             raise NotImplementedError(f"ksp_type={ksp!r}: the device solvers are 'cg', 'pipecg', 'auto' (and 'preonly' = tight cg)")
         norm = NORM[str(opts.get("ksp_norm_type", "default"))]
@@ -150,8 +151,20 @@ class MonodomainModel:
             n_sm = self._ctx.device_info()["n_sm"]
             per_rank = self._mesh.index_map.size_global / max(self._mesh.comm.size, 1)  # the same number on every rank
             ksp = "pipecg" if per_rank <= (n_sm - 1) * 512 else "cg"
+            # Polynomial (Chebyshev-Jacobi) preconditioning trades extra dataflow-synchronised SpMVs (~1.6 us each) for fewer
+            # reductions.  One GPU: a reduction costs ~2.1 us, so it does not pay (measured: 72 vs 63 us/step) and stays
+            # opt-in.  Several GPUs: every reduction also crosses NVLink (+2.4 us) -> 3 steps win (65 vs 74 us/step at 2 GPUs).
+            if ksp == "pipecg" and pc not in PC and self._mesh.comm.size > 1:
+                pc_id = PC["chebyshev"]
+        if pc_id == PC["chebyshev"] and ksp != "pipecg":
+            raise NotImplementedError("pc_type 'chebyshev' is implemented in the pipelined driver: use ksp_type 'pipecg' or 'auto'")
         self._ksp_type = 1 if ksp == "pipecg" else 0  # MONO_KSP_PIPECG / MONO_KSP_CG
         self.ksp_type_used = ksp
+        self.pc_type_used = {v: k for k, v in PC.items()}[pc_id]
+        import os
+
+        self._cheb = (int(opts.get("pc_chebyshev_steps", os.environ.get("MONO_CHEB_STEPS", 3))),
+                      float(opts.get("pc_chebyshev_kappa", os.environ.get("MONO_CHEB_KAPPA", 4.0))))
         return rtol, atol, max_it, pc_id, norm, x0
 
     def _setup_device(self) -> None:
@@ -163,14 +176,15 @@ class MonodomainModel:
         indptr, indices, mass, stiff = fem.assemble_p1_local(mesh, self._M)
         ctx.pde_set_matrices(imap.size_local, imap.num_ghosts, indptr, indices, mass, stiff)
         self._nnz_per_row = len(indices) / max(imap.size_local, 1)
+        rtol, atol, max_it, pc_id, norm, x0 = self._solver_settings()
+        ctx.pde_set_chebyshev(*self._cheb)  # before pde_config / set_halo: the number of exchange buffers depends on it
+        ctx.pde_config(float(self.C_m), float(self.parameters["theta"]), rtol, atol, max_it, pc_id, norm, x0)
+        ctx.pde_set_ksp_type(self._ksp_type)
         if mesh.comm.size > 1:
             from .dist import init_comm
 
             init_comm(ctx, mesh.comm)
             ctx.set_halo(imap.nbr_ranks, imap.send_ptr, imap.send_idx, imap.recv_ptr)
-        rtol, atol, max_it, pc_id, norm, x0 = self._solver_settings()
-        ctx.pde_config(float(self.C_m), float(self.parameters["theta"]), rtol, atol, max_it, pc_id, norm, x0)
-        ctx.pde_set_ksp_type(self._ksp_type)
         self._stim_ids: list[int] = []
         self._stim_amp: list[float] = []
         for s in self._I_s:

@@ -25,7 +25,8 @@ POINTS = {  # demos/niederer_benchmark.py:233-243
 
 
 def setup(dx: float = 0.2, comm=None, rtol: float | None = None, initial_guess_previous: bool = False, monitor=None,
-          L=(20.0, 7.0, 3.0), probes: bool = True, scheme: str = "generalized_rush_larsen", ksp_type: str = "cg"):
+          L=(20.0, 7.0, 3.0), probes: bool = True, scheme: str = "generalized_rush_larsen", ksp_type: str = "cg",
+          pc_type: str | None = None):
     """Returns (solver, info).  rtol None = PETSc's default 1e-5 as the demo runs it (:182-188)."""
     comm = comm or fem.COMM_SELF
     monitor = monitor or NullMonitor()
@@ -39,7 +40,9 @@ def setup(dx: float = 0.2, comm=None, rtol: float | None = None, initial_guess_p
     I_s = stimulation.define_stimulus(mesh=mesh, chi=cond["chi"], time=time, subdomain_data=tags, marker=1, mesh_unit="mm",
                                       amplitude=50_000.0)
     M = conductivities.define_conductivity_tensor(f0=geo.f0, **cond)
-    opts = {"ksp_type": ksp_type, "pc_type": "hypre", "pc_hypre_type": "boomeramg"}
+    opts = {"ksp_type": ksp_type, "pc_type": "hypre", "pc_hypre_type": "boomeramg"}  # as the demo asks (:182-188)
+    if pc_type is not None:
+        opts["pc_type"] = pc_type
     if rtol is not None:
         opts["ksp_rtol"] = rtol
     params = {"petsc_options": opts, "initial_guess_previous": initial_guess_previous}

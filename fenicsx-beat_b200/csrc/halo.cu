@@ -39,6 +39,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   std::string error;
 };
 
@@ -76,6 +77,7 @@ bool nccl_load() {
   g_nccl.Send = reinterpret_cast<decltype(g_nccl.Send)>(sym("ncclSend"));
   g_nccl.Recv = reinterpret_cast<decltype(g_nccl.Recv)>(sym("ncclRecv"));
   g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
   if (!ok) return false;
   g_nccl.handle = h;
   return true;
@@ -98,7 +100,7 @@ __global__ void pack_kernel(int64_t n, const int32_t* __restrict__ idx, const do
 struct PeerMeta {
   cudaIpcMemHandle_t handle;   // of the rank's exchange allocation
   int64_t n_owned, n_ghost;
-  int64_t off_t1, off_xg, off_xrecs, n_recs;  // layout of that allocation, in 16-byte records
+  int64_t nb, nl, off_xg, off_xrecs, n_recs;  // layout of that allocation, in 16-byte records: nb buffers of nl, ...
   int64_t ghost_off[kMaxRanks];  // where the ghosts owned by rank q start in this rank's ghost block (-1: none)
   int64_t ghost_cnt[kMaxRanks];
 };
@@ -142,6 +144,20 @@ int halo_refresh(mono_ctx* c, double* vec) {
   }
   MONO_NCCL(c, g_nccl.GroupEnd());
   c->launches++;
+  return MONO_OK;
+}
+
+int halo_allreduce_max(mono_ctx* c, double* v) {
+  if (c->nranks <= 1) return MONO_OK;
+  if (!c->comm) return mono_fail(c, MONO_E_INVALID, "multi-rank context without communicator (mono_comm_init)");
+  double* d = nullptr;
+  MONO_CUDA(c, cudaMalloc(&d, sizeof(double)));
+  MONO_CUDA(c, cudaMemcpyAsync(d, v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  MONO_NCCL(c, g_nccl.AllReduce(d, d, 1, ncclDouble, ncclMax, (ncclComm_t)c->comm, c->stream));
+  c->launches++;
+  MONO_CUDA(c, cudaMemcpyAsync(v, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d);
   return MONO_OK;
 }
 
@@ -207,7 +223,8 @@ int mono_set_halo(mono_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_
   MONO_CUDA(c, cudaIpcGetMemHandle(&mine.handle, c->exch));
   mine.n_owned = c->n_owned;
   mine.n_ghost = c->n_ghost;
-  mine.off_t1 = c->exch_off_t1;
+  mine.nb = c->exch_nb;
+  mine.nl = c->exch_nl;
   mine.off_xg = c->exch_off_xg;
   mine.off_xrecs = c->exch_off_xrecs;
   mine.n_recs = c->exch_recs;
@@ -251,7 +268,8 @@ int mono_set_halo(mono_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_
 
   // ---- send table: the i-th value we send to neighbour q lands in the i-th ghost q holds from us -----------------
   std::vector<int32_t> rows;
-  std::vector<void*> d0, d1, dx;
+  std::vector<std::vector<void*>> dt((size_t)c->exch_nb);
+  std::vector<void*> dx;
   for (int k = 0; k < n_nbr; ++k) {
     const int q = nbr_ranks[k];
     const int64_t cnt = send_ptr[k + 1] - send_ptr[k];
@@ -259,16 +277,18 @@ int mono_set_halo(mono_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_
       return mono_fail(c, MONO_E_INVALID,
                        "halo mismatch: this rank sends " + std::to_string(cnt) + " dofs to rank " + std::to_string(q) +
                            " but that rank holds " + std::to_string(all[q].ghost_cnt[c->rank]) + " ghosts owned by it");
+    if (all[q].nb != c->exch_nb)
+      return mono_fail(c, MONO_E_INVALID, "ranks disagree on the preconditioner (number of exchange buffers): configure the "
+                                          "PDE stage identically on every rank before mono_set_halo");
     SyncRec* base = static_cast<SyncRec*>(c->peer_base[q]);
     for (int64_t i = 0; i < cnt; ++i) {
       const int64_t g = all[q].ghost_off[c->rank] + i;  // index in q's ghost block
       rows.push_back(send_idx[send_ptr[k] + i]);
-      d0.push_back(base + all[q].n_owned + g);
-      d1.push_back(base + all[q].off_t1 + all[q].n_owned + g);
+      for (int b = 0; b < c->exch_nb; ++b) dt[(size_t)b].push_back(base + b * all[q].nl + all[q].n_owned + g);
       dx.push_back(base + all[q].off_xg + g);
     }
   }
-  int rc = pde_build_send_table(c, rows, d0, d1, dx);
+  int rc = pde_build_send_table(c, rows, dt, dx);
   if (rc) return rc;
   c->peers_ready = true;
   return MONO_OK;

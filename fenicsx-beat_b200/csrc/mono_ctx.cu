@@ -165,7 +165,8 @@ int mono_ctx_destroy(mono_ctx* c) {
   for (void* p : {(void*)c->states, (void*)c->v_ode, (void*)c->params_dev, (void*)c->slice_ptr, (void*)c->cols,
                   (void*)c->mass, (void*)c->stiff, (void*)c->A, (void*)c->B, (void*)c->dinv, (void*)c->x,
                   (void*)c->v_prev, (void*)c->work[0], (void*)c->work[1], (void*)c->work[2], (void*)c->work[3],
-                  (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->stim_vec,
+                  (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->work[8], (void*)c->work[9],
+                  (void*)c->stim_vec,
                   (void*)c->gen_state, (void*)c->send_of_row_dev, (void*)c->send_ents_dev,
                   (void*)c->recs, (void*)c->timeline_dev,
                   (void*)c->ksp_dev, (void*)c->probes_dev,
@@ -382,7 +383,7 @@ int mono_pde_set_matrices(mono_ctx* c, int64_t n_owned, int64_t n_ghost, const i
 int mono_pde_config(mono_ctx* c, double C_m, double theta, double rtol, double atol, int max_it, int pc_type, int norm_type,
                     int x0_mode) {
   MONO_CHECK(c, theta >= 0.0 && theta <= 1.0, "theta outside [0,1]");
-  MONO_CHECK(c, pc_type == MONO_PC_NONE || pc_type == MONO_PC_JACOBI, "unknown pc_type");
+  MONO_CHECK(c, pc_type == MONO_PC_NONE || pc_type == MONO_PC_JACOBI || pc_type == MONO_PC_CHEBYSHEV, "unknown pc_type");
   MONO_CHECK(c, norm_type >= 0 && norm_type <= 2, "unknown norm_type");
   MONO_CHECK(c, x0_mode == MONO_X0_ZERO || x0_mode == MONO_X0_PREVIOUS, "unknown x0_mode");
   MONO_CHECK(c, max_it >= 0, "negative max_it");
@@ -395,7 +396,25 @@ int mono_pde_config(mono_ctx* c, double C_m, double theta, double rtol, double a
   c->norm_type = norm_type;
   c->x0_mode = x0_mode;
   c->have_dt = false;  // matrices depend on C_m / theta / pc
+  if (c->has_pde) {
+    const int nb = pc_type == MONO_PC_CHEBYSHEV ? 3 * c->cheb_k : 2;
+    if (nb != c->exch_nb) {  // the polynomial preconditioner exchanges one vector per step: more tagged buffers
+      MONO_CHECK(c, !c->peers_ready, "choose the preconditioner before mono_set_halo (peers have mapped the exchange buffers)");
+      return pde_setup_launch_config(c);
+    }
+  }
   return MONO_OK;
+}
+
+int mono_pde_set_chebyshev(mono_ctx* c, int steps, double kappa) {
+  MONO_CHECK(c, steps >= 1 && steps <= kMaxCheb, "chebyshev steps must be 1..4");
+  MONO_CHECK(c, kappa > 1.0, "kappa must exceed 1");
+  const bool resize = steps != c->cheb_k && c->pc_type == MONO_PC_CHEBYSHEV && c->has_pde;
+  MONO_CHECK(c, !(resize && c->peers_ready), "choose the preconditioner before mono_set_halo");
+  c->cheb_k = steps;
+  c->cheb_kappa = kappa;
+  c->have_dt = false;
+  return resize ? pde_setup_launch_config(c) : MONO_OK;
 }
 
 int mono_pde_set_ksp_type(mono_ctx* c, int ksp_type) {

@@ -36,6 +36,8 @@ struct alignas(16) SyncRec {
 };
 
 constexpr int kMaxRanks = 16;  // ranks of one multi-GPU run (one node)
+constexpr int kMaxCheb = 4;    // Chebyshev steps of the polynomial preconditioner (1 = Jacobi)
+constexpr int kMaxTb = 3 * kMaxCheb;  // tagged exchange buffers (pde_kernels.cu)
 
 struct ProbeDev {
   int n;           // nodes in this probe (<= 4)
@@ -80,11 +82,14 @@ struct mono_ctx {
   double *mass = nullptr, *stiff = nullptr, *A = nullptr, *B = nullptr;  // sell_nnz each
   double* dinv = nullptr;                // 1/diag(A) (or 1 for PC none), n_owned
   double *x = nullptr, *v_prev = nullptr;  // solution and previous solution, n_local each
-  double* work[8] = {};                    // thread-private CG vectors in global memory (streaming mode only, lazy)
+  double* work[10] = {};                   // thread-private CG vectors in global memory (streaming mode only, lazy)
   // everything a peer rank writes into lives in ONE allocation (exported with CUDA IPC): see pde_setup_launch_config
   SyncRec* exch = nullptr;
-  int64_t exch_recs = 0, exch_off_t1 = 0, exch_off_xg = 0, exch_off_xrecs = 0;  // offsets in records
-  SyncRec *t0 = nullptr, *t1 = nullptr;    // the exchanged CG vector, tagged {value, generation}, n_local each
+  int64_t exch_recs = 0, exch_nl = 0, exch_off_xg = 0, exch_off_xrecs = 0;  // sizes / offsets in records
+  int exch_nb = 2;                         // tagged exchange buffers of exch_nl records each, at the start of `exch`
+  int cheb_k = 3;                          // Chebyshev steps when pc_type == MONO_PC_CHEBYSHEV
+  double cheb_kappa = 4.0;                 // interval [b/kappa, b], b = Gershgorin bound of D^-1 A
+  double cheb_inv_theta = 1.0, cheb_c1[kMaxCheb] = {}, cheb_c2[kMaxCheb] = {}, gershgorin = 0.0;
   SyncRec* xg = nullptr;                   // landing zone of the neighbours' final x values (n_ghost)
   SyncRec* xrecs = nullptr;                // cross-rank reduction records [2][4][kMaxRanks]
   unsigned long long* gen_state = nullptr; // device-resident generation counter of the persistent kernels
@@ -170,9 +175,10 @@ int pde_setup_launch_config(mono_ctx* c);
 int probes_launch(mono_ctx* c, double t0);
 int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync);
 
-int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<void*>& dst_t0,
-                         const std::vector<void*>& dst_t1, const std::vector<void*>& dst_xg);
+int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<std::vector<void*>>& dst_t,
+                         const std::vector<void*>& dst_xg);
 
 // halo.cu
 int halo_refresh(mono_ctx* c, double* vec);  // owner -> ghost copy of an n_local vector through NCCL (no-op for 1 rank)
 int halo_destroy(mono_ctx* c);
+int halo_allreduce_max(mono_ctx* c, double* v);  // max over ranks through the bootstrap communicator (set-up only)

@@ -48,13 +48,15 @@ constexpr int kSlice = 32;
 constexpr int kPdeThreads = 512;
 constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
-constexpr int kMaxResidentRows = 5;   // rows per thread whose CG vectors fit in shared memory (10 x 8 B each)
+constexpr int kMaxResidentRows = 4;   // rows per thread whose CG vectors fit in shared memory (12 x 8 B each)
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
 typedef unsigned long long u64;
+__constant__ unsigned g_poll_ns = 0;     // back-off between two polls of a tagged element (experiments: MONO_POLL_NS)
+__constant__ unsigned g_settle_ns = 0;   // pause before gathering a vector that was published a moment ago (MONO_SETTLE_NS)
 
 // where one owned boundary value goes on ONE neighbour rank (peer-mapped addresses of its ghost slot)
 struct SendEnt {
-  SyncRec* t[2];
+  SyncRec* t[kMaxTb];
   SyncRec* xg;
   int32_t next;  // next entry of the same row (a dof can be a ghost on several ranks), -1 ends the list
   int32_t pad;
@@ -69,8 +71,12 @@ struct PdeArgs {
   const double* dinv;
   const double* v_prev;
   double* x;                        // solution (owned rows written here at the end)
-  double* work[8];                  // streaming mode: thread-private vectors (n_owned each)
-  SyncRec* tb[2];                   // the exchanged vector, tagged {value, generation}, two buffers of n_local
+  double* work[10];                 // streaming mode: thread-private vectors (n_owned each)
+  SyncRec* tb[kMaxTb];              // exchanged vectors, tagged {value, generation}: 2 buffers of n_local (Jacobi), or
+                                    // 3 sets of cheb_k buffers (Chebyshev: one buffer per polynomial step)
+  int cheb_k;                       // Chebyshev steps of the preconditioner (1 = plain Jacobi)
+  double cheb_inv_theta;            // y_1 = g / theta
+  double cheb_c1[kMaxCheb], cheb_c2[kMaxCheb];  // d_j = c1_j d_{j-1} + c2_j (g - D^-1 A y_j), y_{j+1} = y_j + d_j
   const double* stim_vec;           // dense sum_k a_k(t) s_k over owned rows (valid when has_stim)
   int has_stim;
   int staged;                       // streaming mode with every slice at most kChunk wide: TMA-staged SpMV
@@ -151,6 +157,7 @@ __device__ __forceinline__ double wait_tag(const SyncRec* p, u64 want, int* fail
   const u64 t_begin = global_ns();
   unsigned spins = 0;
   while (true) {
+    if (g_poll_ns > 0) __nanosleep(g_poll_ns);  // thousands of threads polling L2 back to back starve the stores they wait for
     ld_tag<SYS>(p, v, g);
     if (g == want) return v;
     if ((++spins & 255u) == 0u) {
@@ -258,11 +265,41 @@ __device__ __forceinline__ void publish(const PdeArgs& a, int which, int64_t row
   }
 }
 
+// Elements of a gather whose producers are behind: poll ALL of them again, together, until none is left (one L2
+// round trip per pass whatever the number of late elements - waiting for them one after the other cost up to 15
+// round trips per row when SpMVs follow each other without a reduction in between).
+template <bool SYS>
+__device__ __forceinline__ unsigned regather(const SyncRec* tv, const int32_t (&c)[kChunk], double (&g)[kChunk], unsigned late, u64 want,
+                                             int* fail, u64 spin_ns) {
+  u64 t_begin = 0;
+  unsigned passes = 0;
+  while (late) {
+    unsigned still = 0;
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) {
+      if (late & (1u << u)) {
+        u64 t;
+        ld_tag<SYS>(tv + c[u], g[u], t);
+        still |= (t != want ? 1u : 0u) << u;
+      }
+    }
+    late = still;
+    if (late && (++passes & 63u) == 0u) {
+      if (t_begin == 0) t_begin = global_ns();
+      if (*(volatile int*)fail || global_ns() - t_begin > spin_ns) {
+        *fail = 1;
+        break;
+      }
+    }
+  }
+  return late;
+}
+
 // ---- SELL rows ---------------------------------------------------------------------------------------------
 // acc[m] = sum_k val(m, k) * g(col(k)) over the `width` entries of a row.  Entries are fetched in unrolled
 // batches of kChunk so the index loads, then the gathers, are all in flight together.  TAGGED: the gathered
 // vector is an array of {value, generation} pairs and the gather waits until every element carries `want`.
-template <int NM, bool TAGGED, bool SYS, bool EARLY_A, class ColF, class ValF>
+template <int NM, bool TAGGED, bool SYS, bool EARLY_A, bool PARLATE, class ColF, class ValF>
 __device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const void* vec, u64 want, int* fail, u64 spin_ns,
                                          double (&acc)[NM]) {
 #pragma unroll
@@ -293,10 +330,14 @@ __device__ __forceinline__ void sell_row(int width, ColF col, ValF val, const vo
           late |= (t != want ? 1u : 0u) << u;
         }
       }
-      if (late) {  // some producer is behind: wait for exactly those elements
+      if (late) {  // some producers are behind
+        if constexpr (PARLATE) {
+          regather<SYS>(tv, c, g, late, want, fail, spin_ns);
+        } else {  // rare when a reduction separates publish and gather: wait element by element (fewer registers)
 #pragma unroll
-        for (int u = 0; u < kChunk; ++u)
-          if (late & (1u << u)) g[u] = wait_tag<SYS>(tv + c[u], want, fail, spin_ns);
+          for (int u = 0; u < kChunk; ++u)
+            if (late & (1u << u)) g[u] = wait_tag<SYS>(tv + c[u], want, fail, spin_ns);
+        }
       }
     } else {
       const double* dv = static_cast<const double*>(vec);
@@ -424,7 +465,7 @@ struct RowRef {
   int width, lane, slot;
 };
 
-template <bool MATSMEM>
+template <bool MATSMEM, bool PARLATE>
 struct MatA {
   const PdeArgs& a;
   const double* sa;    // [kChunk][kPdeThreads] A entries of the thread's row (MATSMEM)
@@ -434,11 +475,11 @@ struct MatA {
   __device__ __forceinline__ double apply(const RowRef& r, const void* vec, u64 want, int* fail) const {
     double out[1];
     if constexpr (MATSMEM) {
-      sell_row<1, true, SYS, false>(
+      sell_row<1, true, SYS, false, PARLATE>(
           r.width, [&](int k) { return sc[k * kPdeThreads + threadIdx.x]; },
           [&](int, int k) { return sa[k * kPdeThreads + threadIdx.x]; }, vec, want, fail, a.spin_ns, out);
     } else {
-      sell_row<1, true, SYS, true>(
+      sell_row<1, true, SYS, true, PARLATE>(
           r.width, [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); },
           [&](int, int k) { return __ldg(a.A + r.beg + (int64_t)k * kSlice + r.lane); }, vec, want, fail, a.spin_ns, out);
     }
@@ -452,14 +493,14 @@ __device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool 
   auto col = [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); };
   if (x0_prev) {
     double ab[2];
-    sell_row<2, false, false, true>(
+    sell_row<2, false, false, true, false>(
         r.width, col, [&](int m, int k) { return __ldg((m == 0 ? a.B : a.A) + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0,
         &dummy, 0, ab);
     bi = ab[0];
     ax0 = ab[1];
   } else {
     double b1[1];
-    sell_row<1, false, false, true>(
+    sell_row<1, false, false, true, false>(
         r.width, col, [&](int, int k) { return __ldg(a.B + r.beg + (int64_t)k * kSlice + r.lane); }, a.v_prev, 0, &dummy, 0, b1);
     bi = b1[0];
     ax0 = 0.0;
@@ -490,7 +531,7 @@ __device__ __forceinline__ void write_result(const PdeArgs& a, int its, int reas
 }
 
 // Thread-private CG vectors of the rows a thread owns: shared memory (RESIDENT) or global arrays.
-enum { VR = 0, VU, VW, VZ, VQ, VS, VP, VN, VX, VD, NVEC };  // streaming mode: VX aliases a.x, VD aliases a.dinv
+enum { VR = 0, VU, VW, VZ, VQ, VS, VP, VN, VX, VD, VY, VE, NVEC };  // streaming mode: VX aliases a.x, VD aliases a.dinv
 
 template <bool RESIDENT>
 struct VecStore {
@@ -516,6 +557,8 @@ __device__ __forceinline__ VecStore<RESIDENT> make_store(const PdeArgs& a, doubl
   for (int k = 0; k < 8; ++k) V.g[k] = a.work[k];
   V.g[VX] = a.x;
   V.g[VD] = const_cast<double*>(a.dinv);
+  V.g[VY] = a.work[8];
+  V.g[VE] = a.work[9];
   V.sm = dyn_smem;
   V.cap = a.rows_per_thread * kPdeThreads;
   return V;
@@ -579,14 +622,16 @@ __device__ __forceinline__ void finish_reducer(const PdeArgs& a, Scratch& sh, u6
 
 template <bool MULTI>
 __device__ void pipecg_reducer(const PdeArgs& a, Scratch& sh, u64 gen) {
-  double bn[1];
-  reduce_publish<1, MULTI>(bn, a, gen++, sh);
-  const double ttol = fmax(a.rtol * sqrt(fabs(bn[0])), a.atol);
   int its = 0, reason = 0;
-  double rnorm = 0.0;
+  double rnorm = 0.0, ttol = 0.0;
   while (true) {
-    double acc[3];
-    reduce_publish<3, MULTI>(acc, a, gen++, sh);
+    double acc[4];
+    if (its == 0) {  // the first reduction also carries the norm of the right-hand side
+      reduce_publish<4, MULTI>(acc, a, gen++, sh);
+      ttol = fmax(a.rtol * sqrt(fabs(acc[3])), a.atol);
+    } else {
+      reduce_publish<3, MULTI>(reinterpret_cast<double(&)[3]>(acc), a, gen++, sh);
+    }
     rnorm = sqrt(fabs(acc[2]));
     reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(acc[0] == acc[0]) || !(acc[1] == acc[1]));
     if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
@@ -677,6 +722,7 @@ __device__ __forceinline__ void stage_wait() {
         a.x[a.n_owned + g] = wait_tag<true>(a.xg + g, xtag__, &sh.fail, a.spin_ns);                          \
     }                                                                                                        \
     if (sh.fail && threadIdx.x == 0) a.res->error = 1;                                                       \
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.gen_state[1] = vtag; /* every CTA read it at its start */      \
   }
 
 // ---- KSPCG (PETSc semantics): two reductions per iteration ------------------------------------------------
@@ -687,8 +733,8 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
   __syncthreads();
-  u64 gen = a.gen_state[0];  // reduction generations (the same sequence in every CTA and on every rank)
-  u64 vtag = gen;            // generation of the exchanged vector p: <= gen at all times, unique per write
+  u64 gen = a.gen_state[0];   // reduction generations (the same sequence in every CTA and on every rank)
+  u64 vtag = a.gen_state[1] + 1;  // tag of the exchanged vector published last: unique per write, continues across launches
   if (blockIdx.x == a.n_workers) {
     cg_reducer<MULTI>(a, sh, gen);
     return;
@@ -701,7 +747,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   double* sa = dyn_smem + (size_t)NVEC * V.cap;
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
   const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
-  const MatA<MATSMEM> Aop{a, sa, sc};
+  const MatA<MATSMEM, false> Aop{a, sa, sc};
   Stager S{};
   if constexpr (!RESIDENT) {
     if (a.staged) {  // (block-uniform) per-warp stage buffers + mbarriers in the otherwise unused dynamic shared memory
@@ -881,16 +927,23 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
 //   gamma = (r,u) ; delta = (w,u) ; m = M^-1 w ; n = A m ; beta = gamma/gamma_old ;
 //   alpha = gamma / (delta - beta*gamma/alpha_old) ; z = n + beta z ; q = m + beta q ; s = w + beta s ;
 //   p = u + beta p ; x += alpha p ; r -= alpha s ; u -= alpha q ; w -= alpha z
-// Only m (and u once, at start-up) is gathered by neighbour rows.  The partial sums of gamma, delta are
-// posted BEFORE n = A m is computed and the totals are awaited after it.
-template <bool RESIDENT, bool MATSMEM, bool MULTI>
+// The partial sums of gamma, delta are posted BEFORE m and n are computed and the totals are awaited after.
+//
+// Preconditioner M^-1 = p(D^-1 A) D^-1: cheb_k steps of the Chebyshev iteration for D^-1 A y = D^-1 w on
+// [b/kappa, b] started from zero (k = 1: plain Jacobi up to a scale; b = Gershgorin bound of D^-1 A, which keeps
+// M^-1 positive definite whatever kappa is).  Every step is one more SpMV whose operand is exchanged through its own
+// tagged buffer - no reduction - so a degree-k preconditioner trades k-1 cheap dataflow-synchronised SpMVs for
+// ~k times fewer grid-wide reductions, which is what a small mesh is bound by (58 176 rows: 7 -> 3 iterations).
+// Buffers: set s, step j -> tb[s*k + j]; applications alternate between sets 0 and 1 (the reduction of every
+// iteration is the all-to-all dependency that makes the reuse safe), set 2 serves M^-1 b at start-up.
+template <bool RESIDENT, bool MATSMEM, bool MULTI, bool CHEB>
 __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArgs a) {
   extern __shared__ double dyn_smem[];
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
   __syncthreads();
   u64 gen = a.gen_state[0];
-  u64 vtag = gen;
+  u64 vtag = a.gen_state[1] + 1;  // tag of the vector published last (every CTA publishes the same sequence)
   if (blockIdx.x == a.n_workers) {
     pipecg_reducer<MULTI>(a, sh, gen);
     return;
@@ -899,16 +952,49 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
   const int64_t warp_global = (int64_t)(threadIdx.x >> 5) * a.n_workers + blockIdx.x;
   const int64_t warp_stride = (int64_t)a.n_workers * kWarpsPerBlock;
   const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
+  const int K = CHEB ? a.cheb_k : 1;  // compile-time 1 for plain Jacobi: the polynomial code drops out of that build
+  constexpr bool cheb = CHEB;
   const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
   double* sa = dyn_smem + (size_t)NVEC * V.cap;
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
   const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
-  const MatA<MATSMEM> Aop{a, sa, sc};
+  const MatA<MATSMEM, CHEB> Aop{a, sa, sc};
   int nstamp = 0;
   stamp(a, nstamp);
 
-  // ---- P0: b = B v_ (+ stimulus) ; r = b - A x0 ; u = D^-1 r -> buffer 1 (tag vtag) ---------------------------
-  double bn[1] = {0.0};
+  // first Chebyshev iterate of an application to the vector whose Jacobi-scaled own value is gi; published in (set, 0)
+  auto start_app = [&](const RowRef& r, int set, double gi, u64 tag) {
+    if (cheb) {
+      gi *= a.cheb_inv_theta;
+      V.st(VY, r, gi);
+      V.st(VE, r, gi);
+    }
+    publish<MULTI>(a, set * K, r.row, gi, tag);
+  };
+  // steps 1 .. K-1 of the application started in `set` (operand D^-1 * vector SRC); leaves y_K in VY and in (set, K-1)
+  auto cheb_steps = [&](int set, int SRC) {
+    for (int j = 1; j < K; ++j) {
+      const double c1 = a.cheb_c1[j], c2 = a.cheb_c2[j];
+      if (j > 1 && g_settle_ns > 0) __nanosleep(g_settle_ns);
+      OWN_ROWS_BEGIN
+        const double ti = Aop.template apply<MULTI>(r, a.tb[set * K + j - 1], vtag, &sh.fail);
+        if (r.row < a.n_owned) {
+          const double di = V.ld(VD, r);
+          const double dj = fma(c1, V.ld(VE, r), c2 * (di * (V.ld(SRC, r) - ti)));
+          const double yi = V.ld(VY, r) + dj;
+          V.st(VE, r, dj);
+          V.st(VY, r, yi);
+          publish<MULTI>(a, set * K + j, r.row, yi, vtag + 1);
+        }
+      OWN_ROWS_END
+      ++vtag;
+    }
+  };
+
+  // ---- P0: b = B v_ (+ stimulus) ; r = b - A x0 ; first iterate of u = M^-1 r -> set 1 -------------------------
+  const bool need_mb = cheb && a.norm_type != MONO_NORM_UNPRECONDITIONED;  // |b| is measured through M^-1
+  const bool app_b = need_mb && x0_prev;                                    // r0 != b: M^-1 b needs its own application
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};  // gamma, delta, norm^2 of r, norm^2 of b (chosen norm)
   OWN_ROWS_BEGIN
     RowRef g = r;
     if constexpr (MATSMEM) {
@@ -920,50 +1006,78 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
       const double di = __ldg(a.dinv + r.row);
       if constexpr (RESIDENT) V.st(VD, r, di);
       const double ri = x0_prev ? bi - ax0 : bi;
-      const double ui = di * ri;
       V.st(VX, r, x0_prev ? __ldg(a.v_prev + r.row) : 0.0);
       V.st(VR, r, ri);
-      V.st(VU, r, ui);
-      publish<MULTI>(a, 1, r.row, ui, vtag);
-      bn[0] += norm_term(a.norm_type, bi, di * bi);
+      if (!need_mb) acc[3] += norm_term(a.norm_type, bi, di * bi);
+      if (app_b) {
+        V.st(VS, r, bi);
+        start_app(r, 2, di * bi, vtag);
+      } else {
+        if (!cheb) V.st(VU, r, di * ri);
+        start_app(r, 1, di * ri, vtag);
+      }
     }
   OWN_ROWS_END
-  post<1>(bn, a, gen, sh);
+  stage_wait<MATSMEM>();
+  if (app_b) {  // M^-1 b (set 2), then the first iterate of u = M^-1 r0 (set 1)
+    cheb_steps(2, VS);
+    ++vtag;
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) {
+        acc[3] += norm_term(a.norm_type, V.ld(VS, r), V.ld(VY, r));
+        start_app(r, 1, V.ld(VD, r) * V.ld(VR, r), vtag);
+      }
+    OWN_ROWS_END
+  }
+  cheb_steps(1, VR);
   stamp(a, nstamp);
 
-  // ---- P1: w = A u ; m = D^-1 w -> buffer 0 (tag vtag+1) ; gamma, delta, norm (overlaps the reduction of |b|) ----
-  stage_wait<MATSMEM>();
-  double acc[3] = {0.0, 0.0, 0.0};
+  // ---- P1: w = A u ; first iterate of m = M^-1 w -> set 0 ; gamma, delta, norms ------------------------------------
   OWN_ROWS_BEGIN
-    const double wi = Aop.template apply<MULTI>(r, a.tb[1], vtag, &sh.fail);
+    const double wi = Aop.template apply<MULTI>(r, a.tb[1 * K + K - 1], vtag, &sh.fail);
     if (r.row < a.n_owned) {
-      const double ri = V.ld(VR, r), ui = V.ld(VU, r);
+      const double ri = V.ld(VR, r);
+      double ui;
+      if (cheb) {
+        ui = V.ld(VY, r);
+        V.st(VU, r, ui);
+      } else {
+        ui = V.ld(VU, r);
+      }
       V.st(VW, r, wi);
-      publish<MULTI>(a, 0, r.row, V.ld(VD, r) * wi, vtag + 1);
+      start_app(r, 0, V.ld(VD, r) * wi, vtag + 1);
       acc[0] = fma(ri, ui, acc[0]);
       acc[1] = fma(wi, ui, acc[1]);
       acc[2] += norm_term(a.norm_type, ri, ui);
+      if (need_mb && !app_b) acc[3] += norm_term(a.norm_type, ri, ui);  // x0 = 0: b = r0, M^-1 b = u
     }
   OWN_ROWS_END
   ++vtag;
   stamp(a, nstamp);
-  wait<1>(bn, a, gen++, sh);
-  const double ttol = fmax(a.rtol * sqrt(fabs(bn[0])), a.atol);
-  stamp(a, nstamp);
 
   int its = 0, reason = 0;
-  double rnorm = 0.0, gamma_old = 1.0, alpha_old = 1.0;
-  int cur = 0;  // buffer that holds m
+  double rnorm = 0.0, gamma_old = 1.0, alpha_old = 1.0, ttol = 0.0;
+  int cur = 0;  // set that holds the current application (m)
   while (true) {
-    post<3>(acc, a, gen, sh);
+    if (its == 0)
+      post<4>(acc, a, gen, sh);
+    else
+      post<3>(reinterpret_cast<const double(&)[3]>(acc), a, gen, sh);
     stamp(a, nstamp);
-    // n = A m while the reduction is in flight
+    // m = M^-1 w (remaining Chebyshev steps) and n = A m while the reduction is in flight
+    cheb_steps(cur, VW);
+    if (cheb && g_settle_ns > 0) __nanosleep(g_settle_ns);
     OWN_ROWS_BEGIN
-      const double ni = Aop.template apply<MULTI>(r, a.tb[cur], vtag, &sh.fail);
+      const double ni = Aop.template apply<MULTI>(r, a.tb[cur * K + K - 1], vtag, &sh.fail);
       if (r.row < a.n_owned) V.st(VN, r, ni);
     OWN_ROWS_END
     stamp(a, nstamp);
-    wait<3>(acc, a, gen++, sh);
+    if (its == 0) {
+      wait<4>(acc, a, gen++, sh);
+      ttol = fmax(a.rtol * sqrt(fabs(acc[3])), a.atol);
+    } else {
+      wait<3>(reinterpret_cast<double(&)[3]>(acc), a, gen++, sh);
+    }
     stamp(a, nstamp);
     const double gamma = acc[0], delta = acc[1];
     rnorm = sqrt(fabs(acc[2]));
@@ -978,7 +1092,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
       if (r.row < a.n_owned) {
         const double di = V.ld(VD, r);
         double xi = V.ld(VX, r), ri = V.ld(VR, r), ui = V.ld(VU, r), wi = V.ld(VW, r);
-        const double mi = di * wi;
+        const double mi = cheb ? V.ld(VY, r) : di * wi;
         double zi = V.ld(VN, r), qi = mi, si = wi, pi = ui;
         if (!first) {
           zi = fma(beta, V.ld(VZ, r), zi);
@@ -998,7 +1112,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
         V.st(VR, r, ri);
         V.st(VU, r, ui);
         V.st(VW, r, wi);
-        publish<MULTI>(a, cur ^ 1, r.row, di * wi, vtag + 1);
+        start_app(r, cur ^ 1, di * wi, vtag + 1);
         acc[0] = fma(ri, ui, acc[0]);
         acc[1] = fma(wi, ui, acc[1]);
         acc[2] += norm_term(a.norm_type, ri, ui);
@@ -1044,9 +1158,11 @@ __global__ void build_ab_kernel(int64_t nnz, const double* __restrict__ mass, co
   }
 }
 
+// also: *gersh = max_i sum_j |a_ij| / a_ii, the Gershgorin bound of the spectrum of D^-1 A (upper end of the
+// Chebyshev interval; positive doubles order like their bit patterns, so an integer atomicMax does it)
 __global__ void jacobi_kernel(int64_t n_owned, int64_t n_slices, const int64_t* __restrict__ slice_ptr,
                               const int32_t* __restrict__ cols, const double* __restrict__ A,
-                              double* __restrict__ dinv, int pc_type) {
+                              double* __restrict__ dinv, int pc_type, unsigned long long* __restrict__ gersh) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n_owned; row += stride) {
     if (pc_type == MONO_PC_NONE) {
@@ -1057,12 +1173,14 @@ __global__ void jacobi_kernel(int64_t n_owned, int64_t n_slices, const int64_t* 
     const int lane = (int)(row % kSlice);
     const int64_t beg = slice_ptr[s];
     const int width = (int)((slice_ptr[s + 1] - beg) / kSlice);
-    double d = 0.0;
+    double d = 0.0, sabs = 0.0;
     for (int k = 0; k < width; ++k) {
       const int64_t e = beg + (int64_t)k * kSlice + lane;
       if (cols[e] == row) d += A[e];
+      sabs += fabs(A[e]);
     }
     dinv[row] = 1.0 / d;
+    if (gersh != nullptr && d > 0.0) atomicMax(gersh, (unsigned long long)__double_as_longlong(sabs / d));
   }
 }
 
@@ -1148,10 +1266,33 @@ int pde_update_matrices(mono_ctx* c, double dt) {
                                                        dt * (1.0 - c->theta));
     c->launches++;
     const int jb = (int)std::min<int64_t>((c->n_owned + threads - 1) / threads, (int64_t)c->n_sm * 16);
+    MONO_CUDA(c, cudaMemsetAsync(c->gen_state + 2, 0, sizeof(unsigned long long), c->stream));
     jacobi_kernel<<<std::max(jb, 1), threads, 0, c->stream>>>(c->n_owned, c->n_slices, c->slice_ptr, c->cols, c->A,
-                                                             c->dinv, c->pc_type);
+                                                             c->dinv, c->pc_type == MONO_PC_CHEBYSHEV ? MONO_PC_JACOBI : c->pc_type,
+                                                             c->gen_state + 2);
     c->launches++;
     MONO_CUDA(c, cudaGetLastError());
+  }
+  if (c->pc_type == MONO_PC_CHEBYSHEV) {
+    double g = 0.0;
+    MONO_CUDA(c, cudaMemcpyAsync(&g, c->gen_state + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+    int rc = halo_allreduce_max(c, &g);  // one polynomial for the whole (distributed) operator
+    if (rc) return rc;
+    if (!(g > 0.0)) g = 1.0;
+    // Chebyshev iteration on [b/kappa, b] (Saad, Iterative Methods, Alg. 12.1), b with a hair of head room
+    const double b = g * (1.0 + 1e-12), lo = b / c->cheb_kappa;
+    const double theta = 0.5 * (b + lo), delta = 0.5 * (b - lo), sigma = theta / delta;
+    c->cheb_inv_theta = 1.0 / theta;
+    double rho = 1.0 / sigma;
+    for (int j = 1; j < kMaxCheb; ++j) {
+      const double rho_n = 1.0 / (2.0 * sigma - rho);
+      c->cheb_c1[j] = rho_n * rho;
+      c->cheb_c2[j] = 2.0 * rho_n / delta;
+      rho = rho_n;
+    }
+    c->cheb_c1[0] = c->cheb_c2[0] = 0.0;
+    c->gershgorin = g;
   }
   c->cur_dt = dt;
   c->have_dt = true;
@@ -1186,20 +1327,23 @@ int pde_setup_launch_config(mono_ctx* c) {
   //   [ xrecs ]    cross-rank reduction records [2 parities][4 slots][kMaxRanks]
   const int64_t nl = std::max<int64_t>(c->n_local, 32);
   const int64_t ng = std::max<int64_t>(c->n_ghost, 1);
-  c->exch_off_t1 = nl;
-  c->exch_off_xg = 2 * nl;
-  c->exch_off_xrecs = 2 * nl + ng;
-  c->exch_recs = 2 * nl + ng + 8 * kMaxRanks;
-  if (c->exch) cudaFree(c->exch);
+  const int nb = c->pc_type == MONO_PC_CHEBYSHEV ? 3 * c->cheb_k : 2;  // exchange buffers (pde_pipecg_kernel)
+  c->exch_nb = nb;
+  c->exch_nl = nl;
+  c->exch_off_xg = nb * nl;
+  c->exch_off_xrecs = nb * nl + ng;
+  c->exch_recs = nb * nl + ng + 8 * kMaxRanks;
+  if (c->exch) {
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->exch);
+  }
   MONO_CUDA(c, cudaMalloc(&c->exch, sizeof(SyncRec) * c->exch_recs));
   MONO_CUDA(c, cudaMemsetAsync(c->exch, 0, sizeof(SyncRec) * c->exch_recs, c->stream));
-  c->t0 = c->exch;
-  c->t1 = c->exch + c->exch_off_t1;
   c->xg = c->exch + c->exch_off_xg;
   c->xrecs = c->exch + c->exch_off_xrecs;
   if (!c->gen_state) {
     MONO_CUDA(c, cudaMalloc(&c->gen_state, sizeof(unsigned long long) * 4));
-    const unsigned long long init[4] = {1ull, 0ull, 0ull, 0ull};  // generation 0 = "never written"
+    const unsigned long long init[4] = {1ull, 1ull, 0ull, 0ull};  // generation / tag 0 = "never written"
     MONO_CUDA(c, cudaMemcpyAsync(c->gen_state, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   }
@@ -1210,17 +1354,21 @@ int pde_setup_launch_config(mono_ctx* c) {
   c->matsmem = c->resident && c->rows_per_thread == 1 && c->max_width <= kChunk && getenv("MONO_PDE_NO_MATSMEM") == nullptr;
   c->resident_smem = c->resident ? (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double) : 0;
   if (c->matsmem) c->resident_smem += (size_t)kChunk * kPdeThreads * (sizeof(double) + sizeof(int32_t));
-  if (c->matsmem && !(opt_in_smem(pde_pipecg_kernel<true, true, false>, c->resident_smem) &&
+  if (c->matsmem && !(opt_in_smem(pde_pipecg_kernel<true, true, false, false>, c->resident_smem) &&
+                      opt_in_smem(pde_pipecg_kernel<true, true, false, true>, c->resident_smem) &&
                       opt_in_smem(pde_cg_kernel<true, true, false>, c->resident_smem) &&
-                      opt_in_smem(pde_pipecg_kernel<true, true, true>, c->resident_smem) &&
+                      opt_in_smem(pde_pipecg_kernel<true, true, true, false>, c->resident_smem) &&
+                      opt_in_smem(pde_pipecg_kernel<true, true, true, true>, c->resident_smem) &&
                       opt_in_smem(pde_cg_kernel<true, true, true>, c->resident_smem))) {
     c->matsmem = false;
     c->resident_smem = (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double);
   }
   if (c->resident && !c->matsmem &&
-      !(opt_in_smem(pde_pipecg_kernel<true, false, false>, c->resident_smem) &&
+      !(opt_in_smem(pde_pipecg_kernel<true, false, false, false>, c->resident_smem) &&
+        opt_in_smem(pde_pipecg_kernel<true, false, false, true>, c->resident_smem) &&
         opt_in_smem(pde_cg_kernel<true, false, false>, c->resident_smem) &&
-        opt_in_smem(pde_pipecg_kernel<true, false, true>, c->resident_smem) &&
+        opt_in_smem(pde_pipecg_kernel<true, false, true, false>, c->resident_smem) &&
+        opt_in_smem(pde_pipecg_kernel<true, false, true, true>, c->resident_smem) &&
         opt_in_smem(pde_cg_kernel<true, false, true>, c->resident_smem))) {
     c->resident = false;
     c->resident_smem = 0;
@@ -1233,9 +1381,15 @@ int pde_setup_launch_config(mono_ctx* c) {
 template <bool MULTI>
 static const void* pde_kernel_for(const mono_ctx* c) {
   const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
-  if (c->matsmem) return pipe ? (const void*)pde_pipecg_kernel<true, true, MULTI> : (const void*)pde_cg_kernel<true, true, MULTI>;
-  if (c->resident) return pipe ? (const void*)pde_pipecg_kernel<true, false, MULTI> : (const void*)pde_cg_kernel<true, false, MULTI>;
-  return pipe ? (const void*)pde_pipecg_kernel<false, false, MULTI> : (const void*)pde_cg_kernel<false, false, MULTI>;
+  const bool cheb = pipe && c->pc_type == MONO_PC_CHEBYSHEV && c->cheb_k > 1;
+  if (!pipe) {
+    if (c->matsmem) return (const void*)pde_cg_kernel<true, true, MULTI>;
+    if (c->resident) return (const void*)pde_cg_kernel<true, false, MULTI>;
+    return (const void*)pde_cg_kernel<false, false, MULTI>;
+  }
+  if (c->matsmem) return cheb ? (const void*)pde_pipecg_kernel<true, true, MULTI, true> : (const void*)pde_pipecg_kernel<true, true, MULTI, false>;
+  if (c->resident) return cheb ? (const void*)pde_pipecg_kernel<true, false, MULTI, true> : (const void*)pde_pipecg_kernel<true, false, MULTI, false>;
+  return cheb ? (const void*)pde_pipecg_kernel<false, false, MULTI, true> : (const void*)pde_pipecg_kernel<false, false, MULTI, false>;
 }
 
 static void fill_sync_args(const mono_ctx* c, PdeArgs& a) {
@@ -1281,7 +1435,23 @@ static int stim_refresh(mono_ctx* c, double t_eval, int* has_stim) {
   return MONO_OK;
 }
 
+static void push_experiment_knobs() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  unsigned v = 0;
+  if (const char* e = getenv("MONO_POLL_NS")) {
+    v = (unsigned)atoi(e);
+    cudaMemcpyToSymbol(g_poll_ns, &v, sizeof(v));
+  }
+  if (const char* e = getenv("MONO_SETTLE_NS")) {
+    v = (unsigned)atoi(e);
+    cudaMemcpyToSymbol(g_settle_ns, &v, sizeof(v));
+  }
+}
+
 int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
+  push_experiment_knobs();
   int has_stim = 0;
   int rc = stim_refresh(c, t_eval, &has_stim);
   if (rc) return rc;
@@ -1303,9 +1473,17 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   a.dinv = c->dinv;
   a.v_prev = c->v_prev;
   a.x = c->x;
-  for (int k = 0; k < 8; ++k) a.work[k] = c->work[k];
-  a.tb[0] = c->t0;
-  a.tb[1] = c->t1;
+  for (int k = 0; k < 10; ++k) a.work[k] = c->work[k];
+  for (int b = 0; b < kMaxTb; ++b) a.tb[b] = b < c->exch_nb ? c->exch + (int64_t)b * c->exch_nl : nullptr;
+  const bool use_cheb = c->pc_type == MONO_PC_CHEBYSHEV && c->ksp_type == MONO_KSP_PIPECG;
+  a.cheb_k = use_cheb ? c->cheb_k : 1;  // (k == 1 runs the plain Jacobi build: same operator up to the scale 1/theta)
+  a.cheb_inv_theta = c->cheb_inv_theta;
+  for (int j = 0; j < kMaxCheb; ++j) {
+    a.cheb_c1[j] = c->cheb_c1[j];
+    a.cheb_c2[j] = c->cheb_c2[j];
+  }
+  if (c->pc_type == MONO_PC_CHEBYSHEV && !use_cheb)
+    return mono_fail(c, MONO_E_UNSUPPORTED, "the Chebyshev preconditioner is implemented in the pipelined driver: use ksp_type pipecg");
   a.stim_vec = c->stim_vec;
   a.has_stim = has_stim;
   a.rows_per_thread = c->rows_per_thread;
@@ -1357,15 +1535,14 @@ int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync) {
 
 // Send table of the in-kernel halo exchange: entry i says that owned row row[i] is a ghost on some neighbour
 // rank whose (peer-mapped) slots in its two exchange buffers and its x landing zone are dst_*[i].
-int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<void*>& dst_t0,
-                         const std::vector<void*>& dst_t1, const std::vector<void*>& dst_xg) {
+int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<std::vector<void*>>& dst_t,
+                         const std::vector<void*>& dst_xg) {
   const size_t n = row.size();
   std::vector<int32_t> first((size_t)std::max<int64_t>(c->n_owned, 1), -1);
   std::vector<SendEnt> ents(std::max<size_t>(n, 1));
   for (size_t i = 0; i < n; ++i) {
     SendEnt& e = ents[i];
-    e.t[0] = static_cast<SyncRec*>(dst_t0[i]);
-    e.t[1] = static_cast<SyncRec*>(dst_t1[i]);
+    for (int b = 0; b < kMaxTb; ++b) e.t[b] = b < (int)dst_t.size() ? static_cast<SyncRec*>(dst_t[b][i]) : nullptr;
     e.xg = static_cast<SyncRec*>(dst_xg[i]);
     e.next = first[row[i]];
     e.pad = 0;

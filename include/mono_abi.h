@@ -48,6 +48,7 @@ extern "C" {
 /* preconditioners / norms / initial guess of the device CG (maps petsc_options, base_model.py:136-157) */
 #define MONO_PC_NONE 0
 #define MONO_PC_JACOBI 1
+#define MONO_PC_CHEBYSHEV 2 /* polynomial: k Chebyshev steps for D^-1 A on [b/kappa, b], b = Gershgorin bound (pipecg only) */
 #define MONO_NORM_PRECONDITIONED 0 /* PETSc default for KSPCG: ||M^-1 r||_2 */
 #define MONO_NORM_UNPRECONDITIONED 1
 #define MONO_NORM_NATURAL 2        /* sqrt(r . M^-1 r) */
@@ -140,6 +141,10 @@ int mono_pde_set_matrices(mono_ctx *ctx, int64_t n_owned, int64_t n_ghost, const
  * (petsc_options ksp_rtol / ksp_atol / ksp_max_it / pc_type / ksp_norm_type).                      */
 int mono_pde_config(mono_ctx *ctx, double C_m, double theta, double rtol, double atol, int max_it,
                     int pc_type, int norm_type, int x0_mode);
+/* MONO_PC_CHEBYSHEV: number of Chebyshev steps (1..4, default 3; 1 = Jacobi) and kappa (default 4).  Any kappa keeps
+ * the preconditioner positive definite; it only tunes where the polynomial is accurate.  With several ranks call it
+ * (and mono_pde_config) BEFORE mono_set_halo: the number of exchange buffers depends on it. */
+int mono_pde_set_chebyshev(mono_ctx *ctx, int steps, double kappa);
 /* Krylov driver (petsc_options ksp_type "cg" | "pipecg"); default MONO_KSP_CG. */
 int mono_pde_set_ksp_type(mono_ctx *ctx, int ksp_type);
 /* (Re)build A = C_m*Mass + dt*theta*K and B = C_m*Mass - dt*(1-theta)*K; called by mono_pde_step

@@ -16,8 +16,8 @@ for p in (ROOT, os.path.join(ROOT, "fenicsx-beat_b200"), os.path.join(ROOT, "tes
         sys.path.insert(0, p)
 
 
-def run_case(nied, fem, comm, dx, dt, nsteps, theta, ksp, x0_prev, rtol):
-    solver, info = nied.setup(dx=dx, comm=comm, rtol=rtol, ksp_type=ksp, initial_guess_previous=x0_prev, probes=False)
+def run_case(nied, fem, comm, dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc=None):
+    solver, info = nied.setup(dx=dx, comm=comm, rtol=rtol, ksp_type=ksp, initial_guess_previous=x0_prev, probes=False, pc_type=pc)
     solver.theta = theta
     t = 0.0
     for _ in range(nsteps):
@@ -55,8 +55,9 @@ def main():
         dx, dt, nsteps, theta, ksp, x0_prev, rtol, tol = (case[k] for k in ("dx", "dt", "nsteps", "theta", "ksp", "x0_prev", "rtol", "tol"))
         for key, val in case.get("env", {}).items():
             os.environ[key] = val
-        v, s, its, reason, l2g, n_owned = run_case(nied, fem, fem.Comm(rank, world), dx, dt, nsteps, theta, ksp, x0_prev, rtol)
-        vg, sg, itsg, reasong, _, _ = run_case(nied, fem, fem.COMM_SELF, dx, dt, nsteps, theta, ksp, x0_prev, rtol)
+        pc = case.get("pc")
+        v, s, its, reason, l2g, n_owned = run_case(nied, fem, fem.Comm(rank, world), dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc)
+        vg, sg, itsg, reasong, _, _ = run_case(nied, fem, fem.COMM_SELF, dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc)
         for key in case.get("env", {}):
             os.environ.pop(key, None)
         scale = np.abs(vg).max()

@@ -225,3 +225,102 @@ def test_split_steps_niederer_small(ctx_factory, theta_split, ksp):
     assert np.array_equal(ctx.get_v_prev(np.empty(n)), got_v)
     assert pde.state.max() > 0.0, "stimulated corner must have depolarised"
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------- Chebyshev preconditioner
+def _cheb_pcg_numpy(A, b, x0, steps, kappa, rtol, norm):
+    """Plain restatement of KSPCG with M^-1 = p(D^-1 A) D^-1 (Chebyshev iteration on [g/kappa, g], g = Gershgorin
+    bound; the device's mono_pde_set_chebyshev) and PETSc's default convergence test.  Returns (x, its, rnorm)."""
+    d = A.diagonal()
+    dinv = 1.0 / d
+    g = (abs(A).sum(axis=1).A1 / d).max() * (1.0 + 1e-12)
+    lo = g / kappa
+    theta, delta = 0.5 * (g + lo), 0.5 * (g - lo)
+    sigma = theta / delta
+
+    def M(w):
+        gg = dinv * w
+        y = gg / theta
+        dv = y.copy()
+        rho = 1.0 / sigma
+        for _ in range(1, steps):
+            rho_n = 1.0 / (2.0 * sigma - rho)
+            dv = rho_n * rho * dv + (2.0 * rho_n / delta) * (gg - dinv * (A @ y))
+            y = y + dv
+            rho = rho_n
+        return y
+
+    def nrm(r, z):
+        return np.sqrt({0: z @ z, 1: r @ r, 2: abs(r @ z)}[norm])
+
+    x = x0.copy()
+    r = b - A @ x
+    z = M(r)
+    ttol = rtol * nrm(b, M(b))
+    p = z.copy()
+    rz = r @ z
+    its = 0
+    rn = nrm(r, z)
+    while rn > ttol and its < 1000:
+        q = A @ p
+        alpha = rz / (p @ q)
+        x += alpha * p
+        r -= alpha * q
+        z = M(r)
+        its += 1
+        rn = nrm(r, z)
+        rz_new = r @ z
+        p = z + (rz_new / rz) * p
+        rz = rz_new
+    return x, its, rn
+
+
+@pytest.mark.parametrize("steps", [2, 3, 4])
+@pytest.mark.parametrize("x0", [0, 1])
+@pytest.mark.parametrize("norm", [0, 1, 2])
+def test_pde_chebyshev_preconditioner(ctx_factory, steps, x0, norm):
+    """pc_type chebyshev in the pipelined driver: (a) tight solve == LU oracle; (b) at the PETSc-default rtol the
+    iteration count, residual norm and iterate equal the plain NumPy restatement of the same preconditioned CG."""
+    prob = P.niederer_slab(0.5)
+    n = prob["mass"].shape[0]
+    rng = np.random.default_rng(9)
+    v_prev = -85.0 + 120.0 * rng.random(n)
+    dt, kappa = 0.05, 4.0
+    A = (prob["C_m"] * prob["mass"] + 0.5 * dt * prob["stiff"]).tocsr()
+    B = (prob["C_m"] * prob["mass"] - 0.5 * dt * prob["stiff"]).tocsr()
+    idx = np.nonzero(prob["stim_load"])[0]
+    b = B @ v_prev + dt * prob["stim_amp"] * prob["stim_load"]
+    for rtol in (1e-12, 1e-5):
+        ctx = ctx_factory()
+        ctx.pde_set_matrices(n, 0, prob["mass"].indptr, prob["mass"].indices, prob["mass"].data, prob["stiff"].data)
+        ctx.pde_set_chebyshev(steps, kappa)
+        ctx.pde_config(prob["C_m"], 0.5, rtol, 1e-50, 1000, 2, norm, x0)
+        ctx.pde_set_ksp_type(KSP["pipecg"])
+        ctx.stim_add(idx, prob["stim_load"][idx], 0.0, 2.0, prob["stim_amp"])
+        ctx.set_v_prev(v_prev)
+        ctx.pde_step(0.5, 0.5 + dt)
+        got = ctx.get_v(np.empty(n))
+        its, rnorm, reason = ctx.ksp_info()
+        assert reason > 0, (its, rnorm, reason)
+        if rtol < 1e-10:
+            import scipy.sparse.linalg as sla
+
+            exact = sla.spsolve(A.tocsc(), b)
+            assert np.abs(got - exact).max() <= 1e-9 * np.abs(exact).max()
+        else:
+            xr, its_r, rn_r = _cheb_pcg_numpy(A, b, v_prev.copy() if x0 else np.zeros(n), steps, kappa, rtol, norm)
+            assert abs(its - its_r) <= 1, (its, its_r)
+            if its == its_r:
+                assert abs(rnorm - rn_r) <= 1e-5 * rn_r
+                assert np.abs(got - xr).max() <= 1e-9 * np.abs(xr).max()
+        ctx.close()
+
+
+def test_pde_chebyshev_needs_pipecg(ctx_factory):
+    prob = P.niederer_slab(0.5)
+    n = prob["mass"].shape[0]
+    ctx = _pde_ctx(ctx_factory, prob, pc=2, ksp=KSP["cg"])
+    ctx.set_v_prev(np.full(n, -80.0))
+    with pytest.raises(Exception, match="pipecg"):
+        ctx.pde_step(0.0, 0.05)
+    ctx.close()

@@ -7,7 +7,8 @@ import numpy as np
 import beat_b200.niederer as nied
 dx = float(sys.argv[1]) if len(sys.argv) > 1 else 0.05
 ksp = sys.argv[2] if len(sys.argv) > 2 else "cg"
-solver, info = nied.setup(dx=dx, probes=False, ksp_type=ksp)
+pc = sys.argv[3] if len(sys.argv) > 3 else None
+solver, info = nied.setup(dx=dx, probes=False, ksp_type=ksp, pc_type=pc)
 ctx = solver.pde._ctx
 n = info["n_owned"]
 t, dt = 0.0, 0.01
@@ -23,8 +24,8 @@ for rep in range(2):
         names = ["rhs", "red0"] + ["spmv", "red", "axpy", "red", "pupd"] * 20
         bytes_row = {"rhs": 244, "spmv": 212, "axpy": 56, "pupd": 48}
     else:
-        names = ["p0", "p1", "red0"] + ["post", "spmv", "wait", "upd"] * 20
-        bytes_row = {"p0": 244, "p1": 220, "spmv": 212, "upd": 152}
+        names = ["p0+app0", "p1"] + ["upd+post", "m,n=A m", "wait"] * 20
+        bytes_row = {}
     for nm, us in zip(names, d):
         gbs = bytes_row.get(nm, 0) * n / (us * 1e-6) / 1e9 if nm in bytes_row else 0
         print("  %-5s %8.1f us %8.0f GB/s" % (nm, us, gbs))

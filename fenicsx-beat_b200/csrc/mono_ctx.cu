@@ -395,6 +395,7 @@ int mono_pde_config(mono_ctx* c, double C_m, double theta, double rtol, double a
   c->pc_type = pc_type;
   c->norm_type = norm_type;
   c->x0_mode = x0_mode;
+  c->mode_dirty = true;
   c->have_dt = false;  // matrices depend on C_m / theta / pc
   if (c->has_pde) {
     const int nb = pc_type == MONO_PC_CHEBYSHEV ? 3 * c->cheb_k : 2;
@@ -413,6 +414,7 @@ int mono_pde_set_chebyshev(mono_ctx* c, int steps, double kappa) {
   MONO_CHECK(c, !(resize && c->peers_ready), "choose the preconditioner before mono_set_halo");
   c->cheb_k = steps;
   c->cheb_kappa = kappa;
+  c->mode_dirty = true;
   c->have_dt = false;
   return resize ? pde_setup_launch_config(c) : MONO_OK;
 }
@@ -420,6 +422,7 @@ int mono_pde_set_chebyshev(mono_ctx* c, int steps, double kappa) {
 int mono_pde_set_ksp_type(mono_ctx* c, int ksp_type) {
   MONO_CHECK(c, ksp_type == MONO_KSP_CG || ksp_type == MONO_KSP_PIPECG, "unknown ksp_type");
   c->ksp_type = ksp_type;
+  c->mode_dirty = true;
   return MONO_OK;
 }
 

@@ -114,6 +114,7 @@ struct mono_ctx {
   SyncRec* recs = nullptr;
   int pde_blocks = 0, pde_workers = 0, pde_threads = 0, rows_per_thread = 1, max_width = 0;
   unsigned long long* timeline_dev = nullptr;  // measurement: phase time stamps of the last PDE kernel (64 slots)
+  bool mode_dirty = true;           // resident / matsmem / staged must be re-derived (mesh, ksp_type or pc_type changed)
   bool matsmem = false;             // ... and so do the A entries (one row per thread)
   bool resident = false;            // the CG vectors of a CTA's rows fit in shared memory
   bool staged = false;              // streaming mode: SELL slices reach the SpMV through TMA-staged shared memory

@@ -48,7 +48,6 @@ constexpr int kSlice = 32;
 constexpr int kPdeThreads = 512;
 constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
-constexpr int kMaxResidentRows = 4;   // rows per thread whose CG vectors fit in shared memory (12 x 8 B each)
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
 typedef unsigned long long u64;
 __constant__ unsigned g_poll_ns = 0;     // back-off between two polls of a tagged element (experiments: MONO_POLL_NS)
@@ -533,26 +532,39 @@ __device__ __forceinline__ void write_result(const PdeArgs& a, int its, int reas
 // Thread-private CG vectors of the rows a thread owns: shared memory (RESIDENT) or global arrays.
 enum { VR = 0, VU, VW, VZ, VQ, VS, VP, VN, VX, VD, VY, VE, NVEC };  // streaming mode: VX aliases a.x, VD aliases a.dinv
 
-template <bool RESIDENT>
+// Which vectors a kernel keeps per row, and where: KIND 0 = cg (5 vectors), 1 = pipecg/Jacobi (10), 2 = pipecg/Chebyshev
+// (12).  Fewer vectors per row = more rows per thread fit the 227 KB of shared memory (cg: 11 rows/thread = 827 k rows
+// per GPU stay resident, e.g. each GPU's share of a 3.4 M-dof mesh split over 8).
+constexpr int kNvec[3] = {5, 10, 12};
+template <int KIND>
+__device__ __forceinline__ constexpr int vec_slot(int v) {
+  if constexpr (KIND == 0) {
+    return v == VR ? 0 : v == VQ ? 1 : v == VP ? 2 : v == VX ? 3 : 4;  // VD
+  } else {
+    return v;
+  }
+}
+
+template <bool RESIDENT, int KIND>
 struct VecStore {
   double* g[NVEC];
   double* sm;
   int cap;
   __device__ __forceinline__ double ld(int v, const RowRef& r) const {
-    if constexpr (RESIDENT) return sm[v * cap + r.slot];
+    if constexpr (RESIDENT) return sm[vec_slot<KIND>(v) * cap + r.slot];
     return __ldcg(g[v] + r.row);
   }
   __device__ __forceinline__ void st(int v, const RowRef& r, double val) const {
     if constexpr (RESIDENT)
-      sm[v * cap + r.slot] = val;
+      sm[vec_slot<KIND>(v) * cap + r.slot] = val;
     else
       __stcg(g[v] + r.row, val);
   }
 };
 
-template <bool RESIDENT>
-__device__ __forceinline__ VecStore<RESIDENT> make_store(const PdeArgs& a, double* dyn_smem) {
-  VecStore<RESIDENT> V;
+template <bool RESIDENT, int KIND>
+__device__ __forceinline__ VecStore<RESIDENT, KIND> make_store(const PdeArgs& a, double* dyn_smem) {
+  VecStore<RESIDENT, KIND> V;
 #pragma unroll
   for (int k = 0; k < 8; ++k) V.g[k] = a.work[k];
   V.g[VX] = a.x;
@@ -743,8 +755,8 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   const int64_t warp_global = (int64_t)(threadIdx.x >> 5) * a.n_workers + blockIdx.x;
   const int64_t warp_stride = (int64_t)a.n_workers * kWarpsPerBlock;
   const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
-  const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
-  double* sa = dyn_smem + (size_t)NVEC * V.cap;
+  const VecStore<RESIDENT, 0> V = make_store<RESIDENT, 0>(a, dyn_smem);
+  double* sa = dyn_smem + (size_t)kNvec[0] * V.cap;
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
   const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
   const MatA<MATSMEM, false> Aop{a, sa, sc};
@@ -954,8 +966,9 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
   const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
   const int K = CHEB ? a.cheb_k : 1;  // compile-time 1 for plain Jacobi: the polynomial code drops out of that build
   constexpr bool cheb = CHEB;
-  const VecStore<RESIDENT> V = make_store<RESIDENT>(a, dyn_smem);
-  double* sa = dyn_smem + (size_t)NVEC * V.cap;
+  constexpr int KIND = CHEB ? 2 : 1;
+  const VecStore<RESIDENT, KIND> V = make_store<RESIDENT, KIND>(a, dyn_smem);
+  double* sa = dyn_smem + (size_t)kNvec[KIND] * V.cap;
   int32_t* sc = reinterpret_cast<int32_t*>(sa + kChunk * kPdeThreads);
   const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
   const MatA<MATSMEM, CHEB> Aop{a, sa, sc};
@@ -1348,48 +1361,60 @@ int pde_setup_launch_config(mono_ctx* c) {
     MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   }
   if (const char* e = getenv("MONO_SPIN_TIMEOUT_MS")) c->spin_timeout_ms = std::max(1.0, atof(e));
-  // shared-memory residency: the CG vectors of a CTA's rows, and (one row per thread) the A entries too
-  const bool force_stream = getenv("MONO_PDE_STREAM") != nullptr;
-  c->resident = c->rows_per_thread <= kMaxResidentRows && !force_stream;
-  c->matsmem = c->resident && c->rows_per_thread == 1 && c->max_width <= kChunk && getenv("MONO_PDE_NO_MATSMEM") == nullptr;
-  c->resident_smem = c->resident ? (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double) : 0;
-  if (c->matsmem) c->resident_smem += (size_t)kChunk * kPdeThreads * (sizeof(double) + sizeof(int32_t));
-  if (c->matsmem && !(opt_in_smem(pde_pipecg_kernel<true, true, false, false>, c->resident_smem) &&
-                      opt_in_smem(pde_pipecg_kernel<true, true, false, true>, c->resident_smem) &&
-                      opt_in_smem(pde_cg_kernel<true, true, false>, c->resident_smem) &&
-                      opt_in_smem(pde_pipecg_kernel<true, true, true, false>, c->resident_smem) &&
-                      opt_in_smem(pde_pipecg_kernel<true, true, true, true>, c->resident_smem) &&
-                      opt_in_smem(pde_cg_kernel<true, true, true>, c->resident_smem))) {
-    c->matsmem = false;
-    c->resident_smem = (size_t)NVEC * c->rows_per_thread * kPdeThreads * sizeof(double);
-  }
-  if (c->resident && !c->matsmem &&
-      !(opt_in_smem(pde_pipecg_kernel<true, false, false, false>, c->resident_smem) &&
-        opt_in_smem(pde_pipecg_kernel<true, false, false, true>, c->resident_smem) &&
-        opt_in_smem(pde_cg_kernel<true, false, false>, c->resident_smem) &&
-        opt_in_smem(pde_pipecg_kernel<true, false, true, false>, c->resident_smem) &&
-        opt_in_smem(pde_pipecg_kernel<true, false, true, true>, c->resident_smem) &&
-        opt_in_smem(pde_cg_kernel<true, false, true>, c->resident_smem))) {
-    c->resident = false;
-    c->resident_smem = 0;
-  }
-  c->staged = !c->resident && c->max_width <= kChunk && getenv("MONO_PDE_NO_STAGING") == nullptr &&
-              opt_in_smem(pde_cg_kernel<false, false, false>, kStagedSmem) && opt_in_smem(pde_cg_kernel<false, false, true>, kStagedSmem);
+  c->mode_dirty = true;
   return MONO_OK;
 }
 
 template <bool MULTI>
-static const void* pde_kernel_for(const mono_ctx* c) {
-  const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
-  const bool cheb = pipe && c->pc_type == MONO_PC_CHEBYSHEV && c->cheb_k > 1;
+static const void* pde_kernel_tbl(bool pipe, bool cheb, bool resident, bool matsmem) {
   if (!pipe) {
-    if (c->matsmem) return (const void*)pde_cg_kernel<true, true, MULTI>;
-    if (c->resident) return (const void*)pde_cg_kernel<true, false, MULTI>;
+    if (matsmem) return (const void*)pde_cg_kernel<true, true, MULTI>;
+    if (resident) return (const void*)pde_cg_kernel<true, false, MULTI>;
     return (const void*)pde_cg_kernel<false, false, MULTI>;
   }
-  if (c->matsmem) return cheb ? (const void*)pde_pipecg_kernel<true, true, MULTI, true> : (const void*)pde_pipecg_kernel<true, true, MULTI, false>;
-  if (c->resident) return cheb ? (const void*)pde_pipecg_kernel<true, false, MULTI, true> : (const void*)pde_pipecg_kernel<true, false, MULTI, false>;
+  if (matsmem) return cheb ? (const void*)pde_pipecg_kernel<true, true, MULTI, true> : (const void*)pde_pipecg_kernel<true, true, MULTI, false>;
+  if (resident) return cheb ? (const void*)pde_pipecg_kernel<true, false, MULTI, true> : (const void*)pde_pipecg_kernel<true, false, MULTI, false>;
   return cheb ? (const void*)pde_pipecg_kernel<false, false, MULTI, true> : (const void*)pde_pipecg_kernel<false, false, MULTI, false>;
+}
+
+static const void* pde_kernel_for_mode(const mono_ctx* c, bool resident, bool matsmem, bool multi) {
+  const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
+  const bool cheb = pipe && c->pc_type == MONO_PC_CHEBYSHEV && c->cheb_k > 1;
+  return multi ? pde_kernel_tbl<true>(pipe, cheb, resident, matsmem) : pde_kernel_tbl<false>(pipe, cheb, resident, matsmem);
+}
+
+// Where the CG vectors (and the A rows) of this mesh live, for the configured Krylov driver and preconditioner.
+static int pde_select_mode(mono_ctx* c) {
+  const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
+  const bool cheb = pipe && c->pc_type == MONO_PC_CHEBYSHEV && c->cheb_k > 1;
+  const int kind = !pipe ? 0 : cheb ? 2 : 1;
+  const size_t per_row = (size_t)kNvec[kind] * kPdeThreads * sizeof(double);
+  const size_t mat_bytes = (size_t)kChunk * kPdeThreads * (sizeof(double) + sizeof(int32_t));
+  const size_t budget = 226 * 1024;  // 227 KB per CTA minus the kernels' static shared memory
+  const bool multi = c->nranks > 1;
+  const void* k = pde_kernel_for_mode(c, true, false, multi);
+  c->resident = (size_t)c->rows_per_thread * per_row <= budget && getenv("MONO_PDE_STREAM") == nullptr;
+  c->matsmem = c->resident && c->rows_per_thread == 1 && c->max_width <= kChunk && per_row + mat_bytes <= budget &&
+               getenv("MONO_PDE_NO_MATSMEM") == nullptr;
+  c->resident_smem = c->resident ? c->rows_per_thread * per_row + (c->matsmem ? mat_bytes : 0) : 0;
+  c->staged = false;
+  if (c->resident) {
+    k = pde_kernel_for_mode(c, true, c->matsmem, multi);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->resident_smem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      c->resident = c->matsmem = false;
+      c->resident_smem = 0;
+    }
+  }
+  if (!c->resident && !pipe && c->max_width <= kChunk && getenv("MONO_PDE_NO_STAGING") == nullptr) {
+    k = pde_kernel_for_mode(c, false, false, multi);
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmem) == cudaSuccess)
+      c->staged = true;
+    else
+      (void)cudaGetLastError();
+  }
+  c->mode_dirty = false;
+  return MONO_OK;
 }
 
 static void fill_sync_args(const mono_ctx* c, PdeArgs& a) {
@@ -1452,6 +1477,10 @@ static void push_experiment_knobs() {
 
 int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   push_experiment_knobs();
+  if (c->mode_dirty) {
+    int rcm = pde_select_mode(c);
+    if (rcm) return rcm;
+  }
   int has_stim = 0;
   int rc = stim_refresh(c, t_eval, &has_stim);
   if (rc) return rc;
@@ -1487,7 +1516,7 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   a.stim_vec = c->stim_vec;
   a.has_stim = has_stim;
   a.rows_per_thread = c->rows_per_thread;
-  a.staged = (c->staged && !c->resident && c->ksp_type == MONO_KSP_CG) ? 1 : 0;
+  a.staged = c->staged ? 1 : 0;
   a.dt = dt;
   a.rtol = c->rtol;
   a.atol = c->atol;
@@ -1501,7 +1530,7 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   if (multi && !c->peers_ready)
     return mono_fail(c, MONO_E_INVALID, "multi-rank context: call mono_set_halo (on every rank) before stepping the PDE stage");
   void* args[] = {&a};
-  MONO_CUDA(c, cudaLaunchCooperativeKernel(multi ? pde_kernel_for<true>(c) : pde_kernel_for<false>(c),
+  MONO_CUDA(c, cudaLaunchCooperativeKernel(pde_kernel_for_mode(c, c->resident, c->matsmem, multi),
                                            dim3(c->pde_blocks), dim3(c->pde_threads), args,
                                            a.staged ? (size_t)kStagedSmem : c->resident_smem, c->stream));
   c->launches++;

@@ -24,7 +24,7 @@ if PKG not in sys.path:
     sys.path.insert(0, PKG)
 
 from codegen.emit import emit_cuda, emit_host_module  # noqa: E402
-from codegen.odefile import FITZHUGH_NAGUMO_ODE, load_ode, parse_ode  # noqa: E402
+from codegen.odefile import BUILTIN_ODES, load_ode, parse_ode  # noqa: E402
 from codegen.program import SCHEMES, build_program, op_counts  # noqa: E402
 
 # tag -> (model id in the C ABI, path below the odes/ root or None for built-in text)
@@ -32,13 +32,15 @@ MODELS = {
     "fhn": (0, None),
     "tp06": (1, "tentusscher_panfilov_2006/tentusscher_panfilov_2006_epi_cell.ode"),
     "torord": (2, "torord/ToRORd_dynCl_endo.ode"),
+    "simple": (3, None),
 }
 
 
 def load_model(tag: str, odes_root: str):
     mid, rel = MODELS[tag]
     if rel is None:
-        return parse_ode(FITZHUGH_NAGUMO_ODE, "fitzhugh_nagumo"), hashlib.sha256(FITZHUGH_NAGUMO_ODE.encode()).hexdigest()
+        name, text = BUILTIN_ODES[tag]
+        return parse_ode(text, name), hashlib.sha256(text.encode()).hexdigest()
     path = os.path.join(odes_root, rel)
     with open(path, "rb") as fh:
         digest = hashlib.sha256(fh.read()).hexdigest()

@@ -175,3 +175,17 @@ v_th = v_amp*a + v_rest
 I = -s*(c_2/v_amp)*(v - v_rest) + (((c_1/v_amp**2)*(v - v_rest))*(v - v_th))*(-v + v_peak)
 dv_dt = I + i_app
 """
+
+
+# The two-state linear test model of the reference's own splitting tests (tests/test_monodomain_solver.py:25-30,
+# tests/test_odesolver.py:20-49: v' = -s, s' = v, advanced with forward Euler), so that those tests can be run
+# through the device path.  omega = 1 reproduces them exactly (multiplication by 1.0 is exact).
+SIMPLE_OSCILLATOR_ODE = """
+states("simple", v=0.0, s=0.0)
+parameters("simple", omega=1.0)
+expressions("simple")
+dv_dt = -omega*s
+ds_dt = omega*v
+"""
+
+BUILTIN_ODES = {"fhn": ("fitzhugh_nagumo", FITZHUGH_NAGUMO_ODE), "simple": ("simple_oscillator", SIMPLE_OSCILLATOR_ODE)}

@@ -21,6 +21,7 @@
 #define MONO_ODE_MATH 1
 #endif
 #include "generated/fhn.cuh"
+#include "generated/simple.cuh"
 #include "generated/torord.cuh"
 #include "generated/tp06.cuh"
 
@@ -76,6 +77,8 @@ struct OdeArgs {
   };
 MONO_STEP_FN(fhn_fe_fn, fhn_fe, 2)
 MONO_STEP_FN(fhn_grl1_fn, fhn_grl1, 2)
+MONO_STEP_FN(simple_fe_fn, simple_fe, 2)
+MONO_STEP_FN(simple_grl1_fn, simple_grl1, 2)
 MONO_STEP_FN(tp06_fe_fn, tp06_fe, 19)
 MONO_STEP_FN(tp06_grl1_fn, tp06_grl1, 19)
 MONO_STEP_FN(torord_fe_fn, torord_fe, 45)
@@ -193,6 +196,7 @@ int launch_model(mono_ctx* c, const OdeArgs& a) {
 int ode_model_dims(int model_id, int* ns, int* np) {
   switch (model_id) {
     case MONO_MODEL_FHN: *ns = fhn_meta::kNumStates; *np = fhn_meta::kNumParams; return 0;
+    case MONO_MODEL_SIMPLE: *ns = simple_meta::kNumStates; *np = simple_meta::kNumParams; return 0;
     case MONO_MODEL_TP06: *ns = tp06_meta::kNumStates; *np = tp06_meta::kNumParams; return 0;
     case MONO_MODEL_TORORD: *ns = torord_meta::kNumStates; *np = torord_meta::kNumParams; return 0;
   }
@@ -202,6 +206,7 @@ int ode_model_dims(int model_id, int* ns, int* np) {
 int ode_model_num_derived(int model_id, int /*scheme_id*/) {
   switch (model_id) {
     case MONO_MODEL_FHN: return fhn_meta::kNumDerived;
+    case MONO_MODEL_SIMPLE: return simple_meta::kNumDerived;
     case MONO_MODEL_TP06: return tp06_meta::kNumDerived;
     case MONO_MODEL_TORORD: return torord_meta::kNumDerived;
   }
@@ -214,6 +219,8 @@ int ode_launch(mono_ctx* c, double t, double dt, const double* v_in, double* v_o
   switch (c->model_id) {
     case MONO_MODEL_FHN:
       return grl ? launch_model<fhn_grl1_fn, fhn_meta>(c, a) : launch_model<fhn_fe_fn, fhn_meta>(c, a);
+    case MONO_MODEL_SIMPLE:
+      return grl ? launch_model<simple_grl1_fn, simple_meta>(c, a) : launch_model<simple_fe_fn, simple_meta>(c, a);
     case MONO_MODEL_TP06:
       return grl ? launch_model<tp06_grl1_fn, tp06_meta>(c, a) : launch_model<tp06_fe_fn, tp06_meta>(c, a);
     case MONO_MODEL_TORORD:

@@ -41,6 +41,7 @@ extern "C" {
 #define MONO_MODEL_FHN 0    /* FitzHugh-Nagumo, README.md:58-129 */
 #define MONO_MODEL_TP06 1   /* odes/tentusscher_panfilov_2006/tentusscher_panfilov_2006_epi_cell.ode */
 #define MONO_MODEL_TORORD 2 /* odes/torord/ToRORd_dynCl_endo.ode */
+#define MONO_MODEL_SIMPLE 3 /* v' = -omega s, s' = omega v: the linear test model of tests/test_monodomain_solver.py:25-30 */
 
 #define MONO_SCHEME_FORWARD_EULER 0 /* y + dt f */
 #define MONO_SCHEME_GRL1 1          /* generalized Rush-Larsen, first order (gotranx scheme) */

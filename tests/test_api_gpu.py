@@ -286,3 +286,86 @@ def test_niederer_full_config_activation_times():
         assert want[name] >= 0 and got[pid] >= 0, (name, want[name], got[pid])
         assert abs(got[pid] - want[name]) <= dt + 1e-9, (name, got[pid], want[name])
         assert abs(got[pid] - pub[name]) <= 0.02 * pub[name] + dt, (name, got[pid], pub[name])
+
+
+# ---- the reference's splitting tests with its own two-state linear cell model, on the device -------------------
+def _g2(x):
+    return np.cos(2 * np.pi * x[0]) * np.cos(2 * np.pi * x[1])
+
+
+def _simple_split_solver(N, theta=1.0, ksp_rtol=1e-10):
+    beat = _beat()
+    fem = beat.fem
+    mesh = fem.create_unit_square(fem.COMM_SELF, N, N)
+    time = fem.Constant(mesh, 0.0)
+    I_s = fem.Separable(time, _g2, lambda t: 8 * np.pi**2 * np.sin(t), degree=6)  # ac_func, test_monodomain_solver.py:21-22
+    pde = beat.MonodomainModel(time=time, mesh=mesh, M=1.0, I_s=I_s,
+                               params={"petsc_options": {"ksp_type": "cg", "pc_type": "jacobi", "ksp_rtol": ksp_rtol}})
+    m = beat.models.simple
+    init = np.zeros((2, mesh.geometry.x.shape[0]))
+    init[1] = -_g2(mesh.geometry.x.T)  # s_exact at t = 0
+    ode = beat.odesolver.DolfinODESolver(v_ode=fem.Function(pde.V), v_pde=pde.state, fun=m.forward_explicit_euler, init_states=init,
+                                         parameters=m.init_parameter_values(), num_states=2, v_index=0)
+    return beat.MonodomainSplittingSolver(pde=pde, ode=ode, theta=theta), mesh
+
+
+def _l2_error_vs_exact(solver, mesh, N):
+    from oracle import fem as ofem
+
+    pts, cells = ofem.rectangle_mesh(N, N)
+    assert np.allclose(pts, mesh.geometry.x[:, :2])
+    t_eval = float(solver.pde.time.value)  # the reference evaluates v_exact at time.value of the last PDE step
+    return ofem.l2_error(pts, cells, solver.pde.state.x.array_ro, lambda x: _g2(x) * np.sin(t_eval))
+
+
+def test_monodomain_splitting_analytic():
+    """tests/test_monodomain_solver.py:41-87 (P1 ODE space), the reference's bound: L2 error < 0.002."""
+    solver, mesh = _simple_split_solver(50)
+    solver.solve((0.0, 1.0), dt=0.01)
+    assert _l2_error_vs_exact(solver, mesh, 50) < 0.002
+
+
+def test_monodomain_splitting_spatial_convergence():
+    """tests/test_monodomain_solver.py:98-149: dt = 1e-3, T = 1, N = 8, 16, 32 -> mean rate > 1.85."""
+    errors = []
+    for N in (8, 16, 32):
+        solver, mesh = _simple_split_solver(N)
+        solver.solve((0.0, 1.0), dt=0.001)
+        errors.append(_l2_error_vs_exact(solver, mesh, N))
+    rates = [np.log(e1 / e2) / np.log(2) for e1, e2 in zip(errors[:-1], errors[1:])]
+    assert sum(rates) / len(rates) > 1.85, (rates, errors)
+
+
+def test_monodomain_splitting_temporal_convergence():
+    """tests/test_monodomain_solver.py:161-216 (theta_split = 1): N = 150, dt = 1/8, 1/16, 1/32 -> mean rate > 1.0."""
+    errors = []
+    for dt in (1.0 / 8, 1.0 / 16, 1.0 / 32):
+        solver, mesh = _simple_split_solver(150)
+        solver.solve((0.0, 1.0), dt=dt)
+        errors.append(_l2_error_vs_exact(solver, mesh, 150))
+    rates = [np.log(e1 / e2) / np.log(2) for e1, e2 in zip(errors[:-1], errors[1:])]
+    assert sum(rates) / len(rates) > 1.0, (rates, errors)
+
+
+def test_simple_ode_odesystemsolver_rate():
+    """tests/test_odesolver.py:20-49: forward Euler on v' = -s, s' = v from (1, 0): samples at t = 0.1 .. 1.0 against
+    (cos t, sin t), dt = 0.1, 0.01, 0.001 -> error decades per dt decade = 1 +- 0.01."""
+    beat = _beat()
+    m = beat.models.simple
+    x = np.arange(0.1, 1.0 + 0.1, 0.1)
+    sol = np.vstack((np.cos(x), np.sin(x))).T
+    errors = []
+    for dt in (0.1, 0.01, 0.001):
+        ode = beat.odesolver.ODESystemSolver(fun=m.forward_explicit_euler, states=np.array([[1.0], [0.0]]), parameters=m.init_parameter_values())
+        y = np.zeros((len(x), 2))
+        j, t = 0, 0.0
+        for _ in range(int(round(1.0 / dt))):
+            ode.step(t, dt)
+            t += dt
+            if j < len(x) and np.isclose(t, x[j]):
+                y[j, :] = ode.states[:, 0]
+                j += 1
+        assert j == len(x)
+        errors.append(np.linalg.norm(sol - y))
+    rates = [np.log(e1 / e2) / np.log(10) for e1, e2 in zip(errors[:-1], errors[1:])]
+    assert np.allclose(rates, 1, atol=0.01), rates

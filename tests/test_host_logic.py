@@ -1,0 +1,99 @@
+"""Host-side pieces of the drop-in that need no GPU: monitors (reference tests/test_telemetry.py), define_stimulus unit
+rules (tests/test_stimulation.py:111-304), conductivities (src/beat/conductivities.py:63-118)."""
+import json
+import logging
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "fenicsx-beat_b200"))
+from beat_b200 import conductivities, fem, stimulation, telemetry  # noqa: E402
+
+
+class _Ksp:
+    def __init__(self, its, rn, reason):
+        self._v = (its, rn, reason)
+
+    def getIterationNumber(self):
+        return self._v[0]
+
+    def getResidualNorm(self):
+        return self._v[1]
+
+    def getConvergedReason(self):
+        return self._v[2]
+
+
+def test_null_monitor():  # tests/test_telemetry.py:11-23
+    m = telemetry.NullMonitor()
+    with m.track_time("anything"):
+        pass
+    m.record_ksp(_Ksp(3, 1e-6, 2))
+    m.advance_step(0.0, 0.1)
+
+
+def test_performance_monitor_tracking_and_ksp(tmp_path, caplog):  # tests/test_telemetry.py:26-117
+    m = telemetry.PerformanceMonitor(log_frequency=1)
+    with m.track_time("pde_step"):
+        pass
+    with m.track_time("pde_step"):
+        pass
+    assert m.timings["pde_step"] >= 0.0
+    m.record_ksp(_Ksp(5, 1e-7, 2))
+    m.record_ksp(_Ksp(9, 1e-8, -3))
+    assert m.ksp_total_iterations == 14 and m.ksp_max_iterations == 9 and m.ksp_last_iterations == 9
+    with caplog.at_level(logging.INFO):
+        m.advance_step(0.0, 0.1)
+    assert m.step_counter == 1
+    out = tmp_path / "summary.json"
+    m.save_summary(out)
+    data = json.loads(out.read_text())
+    assert data["ksp"]["total_iterations"] == 14 if "ksp" in data else "ksp_total_iterations" in json.dumps(data)
+
+
+def test_define_stimulus_units_and_window():  # tests/test_stimulation.py:253-304 and the unit rules :111-250
+    mesh = fem.create_unit_square(fem.COMM_SELF, 2, 2)
+    cells = fem.locate_entities(mesh, 2, lambda x: np.full(x.shape[1], True))
+    tags = fem.meshtags(mesh, 2, cells, np.full(len(cells), 1, dtype=np.int32))
+    time = fem.Constant(mesh, 0.0)
+    start, duration, amplitude, chi = 1.0, 2.0, 3.0, 2.0
+    stim = stimulation.define_stimulus(mesh=mesh, chi=chi, time=time, amplitude=amplitude, start=start, duration=duration,
+                                       mesh_unit="cm", marker=1, subdomain_data=tags)
+    assert stim.marker == 1
+    load = fem.load_vector(mesh, stim.dZ, stim.marker)  # int phi_i over the marked cells: sums to the area (1)
+    assert np.isclose(load.sum(), 1.0)
+
+    def total(t):
+        time.value = t
+        e = stim.expr
+        on = e.start <= float(time.value) <= e.end
+        return load.sum() * (e.amplitude_now() if on else 0.0)
+
+    assert np.isclose(total(0.0), 0.0)
+    assert np.isclose(total(start), amplitude / chi)
+    assert np.isclose(total(start + duration / 2), amplitude / chi)
+    assert np.isclose(total(start + duration + 1e-6), 0.0)
+    # mm mesh: uA/cm^2 -> uA/mm^2 for a cell stimulus in 2-D (effective dimension 3): factor 1e-2 (niederer_benchmark.py)
+    mm = stimulation.define_stimulus(mesh=mesh, chi=1400.0, time=time, amplitude=50000.0, mesh_unit="mm", marker=1, subdomain_data=tags)
+    assert np.isclose(mm.expr.amplitude_now(), 50000.0 / 1400.0 * 1e-2)
+    with pytest.raises(ValueError):
+        stimulation.define_stimulus(mesh=mesh, chi=1.0, time=time, mesh_unit="inch", marker=1, subdomain_data=tags)
+    stim.assign(7.0)  # Stimulus.assign, stimulation.py:23-24
+    assert stim.expr.amplitude_now() == 7.0
+
+
+def test_conductivities():  # src/beat/conductivities.py:29-118
+    c = conductivities.default_conductivities("Niederer")
+    s_l, s_t = conductivities.get_harmonic_mean_conductivity(**c)
+    assert np.isclose(s_l, 0.17 * 0.62 / (0.17 + 0.62) / 1.4e5 * 1e3)
+    assert np.isclose(s_t, 0.019 * 0.24 / (0.019 + 0.24) / 1.4e5 * 1e3)
+    M = conductivities.define_conductivity_tensor(f0=np.array([1.0, 0.0, 0.0]), **c)
+    assert np.allclose(M, np.diag([s_l, s_t, s_t]))
+    f = np.array([1.0, 1.0, 0.0]) / np.sqrt(2)
+    M2 = conductivities.conductivity_tensor(s_l, s_t, f)
+    assert np.allclose(M2 @ f, s_l * f) and np.allclose(M2, M2.T)
+    with pytest.raises(ValueError):
+        conductivities.default_conductivities("nobody")

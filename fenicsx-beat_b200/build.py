@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("MONO_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

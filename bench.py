@@ -48,6 +48,12 @@ WORKLOADS = {
     "niederer_dx0.5": (0.5, 0.01),
     "niederer_dx0.025": (0.025, 0.01),   # 27.2 M dofs (BASELINE config 4's "~30M")
 }
+# BASELINE config 5 (synthetic LV shell, endocardial surface stimulus, three transmural layers): (n_r, n_mu, n_phi), dt
+LV_WORKLOADS = {
+    "lv_ellipsoid_40k": ((6, 48, 128), 0.01),
+    "lv_ellipsoid_320k": ((12, 128, 192), 0.01),
+    "lv_ellipsoid_1.4M": ((16, 256, 320), 0.01),
+}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -186,13 +192,25 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     comm = fem.Comm(rank, world)
-    dx, dt = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
-
     t_setup = time.perf_counter()
-    Lx = 20.0 * world if args.scaling == "weak" else 20.0
-    solver, info = nied.setup(dx=dx, comm=comm, L=(Lx, 7.0, 3.0), probes=False, ksp_type=args.ksp,
-                              initial_guess_previous=args.x0 == "previous", pc_type=None if args.pc == "auto" else args.pc)
+    is_lv = args.workload in LV_WORKLOADS
+    if is_lv:
+        from beat_b200 import lv_ellipsoid
+
+        (n_r, n_mu, n_phi), dt = LV_WORKLOADS[args.workload]
+        if args.scaling == "weak":
+            n_phi *= world  # finer in phi: one sector of the same size per GPU
+        dx, Lx = 0.0, 0.0
+        solver, info = lv_ellipsoid.setup(n=(n_r, n_mu, n_phi), comm=comm, ksp_type=args.ksp, pc_type=None if args.pc == "auto" else args.pc,
+                                          initial_guess_previous=args.x0 == "previous")
+        geom_txt = f"synthetic LV shell ({n_r}x{n_mu}x{n_phi} hexahedra, Kuhn tets, cell-wise Bishop conductivity tensor, ENDO surface stimulus, 3 layers)"
+    else:
+        dx, dt = WORKLOADS[args.workload]
+        Lx = 20.0 * world if args.scaling == "weak" else 20.0
+        solver, info = nied.setup(dx=dx, comm=comm, L=(Lx, 7.0, 3.0), probes=False, ksp_type=args.ksp,
+                                  initial_guess_previous=args.x0 == "previous", pc_type=None if args.pc == "auto" else args.pc)
+        geom_txt = f"Niederer slab {Lx:g}x7x3 mm, dx={dx} mm"
     ctx = solver.pde._ctx
     args.ksp = solver.pde.ksp_type_used
     n_global, n_owned = info["n_global"], info["n_owned"]
@@ -340,7 +358,7 @@ def run_b200(args):
                 "achieved": pde_bytes / (pde_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": pde_bytes / (pde_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "ms_per_launch": pde_ms, "algorithmic_bytes_per_launch": pde_bytes}
-    roof_ode = {"kernel": "ode_kernel_uniform<tp06_grl1>", "bound": "fp64", "achieved": ode_flop / (ode_ms * 1e-3) / 1e12,
+    roof_ode = {"kernel": "ode_kernel_pernode<tp06_grl1>" if is_lv else "ode_kernel_uniform<tp06_grl1>", "bound": "fp64", "achieved": ode_flop / (ode_ms * 1e-3) / 1e12,
                 "peak": dfma_tflops, "unit": "TFLOP/s (fp64-pipe instructions x2)", "frac": ode_flop / (ode_ms * 1e-3) / 1e12 / dfma_tflops,
                 "traffic": None, "peak_source": "mono_bench_dfma (measured DFMA rate, this run)", "ms_per_launch": ode_ms,
                 "hbm_gbs": ode_bytes / (ode_ms * 1e-3) / 1e9}
@@ -357,11 +375,11 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, 3),
         "ms_per_step": ms_flushed / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: Niederer slab {Lx:g}x7x3 mm, dx={dx} mm, {n_global} nodes "
+        "config": {"workload": f"{args.workload}: {geom_txt}, {n_global} nodes "
                                f"({n_owned} owned by rank 0), TP06 GRL1, Godunov split + CN diffusion "
                                f"({solver.pde.pc_type_used}-preconditioned {args.ksp}, rtol 1e-5, x0={'0' if args.x0 == 'zero' else 'v_'}), dt={dt} ms", "nodes": n_global,
                    "l2": "flushed (256 MiB memset) between timed steps; flush outside the CUDA events",
-                   "parallelism": f"x-slab partition, {world} rank(s), one per GPU"},
+                   "parallelism": f"{'phi-sector' if is_lv else 'x-slab'} partition, {world} rank(s), one per GPU"},
         "warm_l2": {"value": n_global * K / (ms_warm * 1e-3), "ms_per_step": ms_warm / K,
                     "note": "same K steps back to back, no L2 flush"},
         "x0_previous": fast,
@@ -375,7 +393,7 @@ def run_b200(args):
         "clocks": clk, "setup_s": setup_s, "v_max_mV": v_max,
     }
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not is_lv:
             r = cpu_run(dx, dt, steps=2000, warmup=2, budget_s=20.0)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
@@ -393,7 +411,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="niederer_dx0.2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="niederer_dx0.2", choices=sorted(WORKLOADS) + sorted(LV_WORKLOADS))
     ap.add_argument("--ksp", default="auto", choices=["auto", "cg", "pipecg"],
                     help="Krylov driver of the diffusion solve (PETSc names; auto = pipecg while the CG vectors fit in shared "
                          "memory, cg beyond - same iterates in exact arithmetic)")

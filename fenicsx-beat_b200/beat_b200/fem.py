@@ -144,6 +144,9 @@ class Mesh:
             cand = uniq[counts == 1]
             # a facet seen once locally may be interior to the global mesh (its other cell lives on another
             # rank); such a facet has only ghost/boundary vertices.  Structured generators pass a predicate.
+            on_ids = self.info.get("on_boundary_ids")
+            if on_ids is not None:  # structured generators that know the exterior from the vertex indices
+                cand = cand[np.asarray(on_ids(self.index_map.local_to_global[cand]), dtype=bool)]
             on_bnd = self.info.get("on_boundary")
             if on_bnd is not None:
                 keep = np.ones(cand.shape[0], dtype=bool)
@@ -486,6 +489,59 @@ def assemble_p1_box(mesh: "BoxMesh", Mv: np.ndarray):
     counts = valid.sum(axis=1)
     indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return indptr, cols[valid], mass[valid], stiff[valid]
+
+
+def create_lv_ellipsoid(comm: Comm, n_r: int, n_mu: int, n_phi: int, r_short_endo: float = 2.5, r_short_epi: float = 3.5,
+                        r_long_endo: float = 9.0, r_long_epi: float = 9.7, base: float = 0.0, apex_cut: float = 0.25) -> Mesh:
+    """Synthetic truncated prolate-ellipsoid shell in the spirit of demos/lv_endocardial.py:35-58 (radii from there; the
+    reference builds it with cardiac_geometries/gmsh, which are not available here): a structured (transmural, mu,
+    phi) grid, periodic in phi, Kuhn-split into tetrahedra.  x = r_long cos(mu) is the long axis, the apex (mu = -pi)
+    is cut off at mu = -pi + apex_cut to avoid the degenerate pole.  Partition: phi sectors (periodic: the first and
+    the last rank are neighbours).  Vertex id = (i_r (n_mu+1) + i_mu) n_phi + i_phi; mesh.info carries the index maps
+    needed for markers (transmural layer of a vertex, exterior surfaces)."""
+    starts = _partition_1d(n_phi, comm.size)
+    lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
+    cols = np.arange(lo - 1, hi) % n_phi if comm.size > 1 else np.arange(n_phi)  # hexahedra columns touching owned vertices
+    cols = np.unique(cols)
+    ir, im, ip = np.meshgrid(np.arange(n_r), np.arange(n_mu), cols, indexing="ij")
+    ir, im, ip = ir.ravel(), im.ravel(), ip.ravel()
+
+    def vid(a, b, c):
+        return (a * (n_mu + 1) + b) * n_phi + (c % n_phi)
+
+    corner = {(da, db, dc): vid(ir + da, im + db, ip + dc) for da in (0, 1) for db in (0, 1) for dc in (0, 1)}
+    tets = []
+    for perm in _KUHN_PERMS:
+        off = [0, 0, 0]
+        verts = [corner[tuple(off)]]
+        for ax in perm:
+            off[ax] += 1
+            verts.append(corner[tuple(off)])
+        tets.append(np.stack(verts, axis=1))
+    cells = np.concatenate(tets, axis=0).astype(np.int64)
+    mu0, mu1_endo, mu1_epi = -math.pi + apex_cut, -math.acos(base / r_long_endo), -math.acos(base / r_long_epi)
+
+    def decode(g):
+        g = np.asarray(g)
+        return g // ((n_mu + 1) * n_phi), (g // n_phi) % (n_mu + 1), g % n_phi
+
+    def coords(g):
+        a, b, c = decode(g)
+        lam = a / n_r
+        rs = r_short_endo + lam * (r_short_epi - r_short_endo)
+        rl = r_long_endo + lam * (r_long_epi - r_long_endo)
+        mu = mu0 + (b / n_mu) * ((mu1_endo + lam * (mu1_epi - mu1_endo)) - mu0)
+        phi = 2.0 * math.pi * c / n_phi
+        return np.stack([rl * np.cos(mu), rs * np.sin(mu) * np.cos(phi), rs * np.sin(mu) * np.sin(phi)], axis=1)
+
+    def on_boundary_ids(fg):  # facet (nf, 3) global vertex ids -> exterior?
+        a, b, _ = decode(fg)
+        return (np.all(a == 0, axis=1) | np.all(a == n_r, axis=1) | np.all(b == 0, axis=1) | np.all(b == n_mu, axis=1))
+
+    n_global = (n_r + 1) * (n_mu + 1) * n_phi
+    mesh = _build_local(comm, cells, coords, lambda g: np.searchsorted(starts, np.asarray(g) % n_phi, side="right") - 1, n_global, 3,
+                        {"kind": "lv_ellipsoid", "n": (n_r, n_mu, n_phi), "on_boundary_ids": on_boundary_ids, "decode": decode})
+    return mesh
 
 
 # ---------------------------------------------------------------------------- entities and tags

@@ -50,3 +50,41 @@ def get_3D_slab_geometry(comm, Lx: float, Ly: float, Lz: float, dx: float, trans
     mesh = get_3D_slab_mesh(comm, dx, Lx, Ly, Lz)
     f0, s0, n0 = get_3D_slab_microstructure(mesh, transverse)
     return Geometry(mesh=mesh, f0=f0, s0=s0, n0=n0)
+
+
+def get_lv_ellipsoid_geometry(comm, n_r: int = 4, n_mu: int = 24, n_phi: int = 32, fiber_angle_endo: float = 60.0,
+                              fiber_angle_epi: float = -60.0, **radii) -> Geometry:
+    """Synthetic LV shell with the markers and the fibre field the reference's demos/lv_endocardial.py takes from
+    cardiac_geometries (:35-75): facet tags ENDO / EPI / BASE / APEX (the cut), a vertex function ``endo_epi`` in info
+    (1 endo / 2 mid / 3 epi third of the wall, for DolfinMultiODESolver), and a CELL-WISE fibre direction whose helix
+    angle turns linearly from fiber_angle_endo to fiber_angle_epi across the wall (f0: (ncell, 3) array)."""
+    mesh = fem.create_lv_ellipsoid(comm, n_r, n_mu, n_phi, **radii)
+    decode = mesh.info["decode"]
+    l2g = mesh.index_map.local_to_global
+    a, b, _ = decode(l2g)
+    markers = {"ENDO": (1, 2), "EPI": (2, 2), "BASE": (3, 2), "APEX": (4, 2)}
+    fac = mesh.boundary_facets()
+    fa, fb = a[fac], b[fac]
+    val = np.zeros(fac.shape[0], dtype=np.int32)
+    val[np.all(fb == 0, axis=1)] = 4
+    val[np.all(fb == n_mu, axis=1)] = 3
+    val[np.all(fa == n_r, axis=1)] = 2
+    val[np.all(fa == 0, axis=1)] = 1
+    ffun = fem.meshtags(mesh, 2, np.arange(fac.shape[0], dtype=np.int32), val)
+    layer = np.minimum(3 * a // (n_r + 1), 2) + 1  # vertex layer 1..3
+    mesh.info["endo_epi"] = layer.astype(np.float64)
+    # fibres at the cell centroids: circumferential / longitudinal frame of the local ellipsoid coordinates
+    X = mesh.geometry.x[mesh.cells].mean(axis=1)
+    lam = a[mesh.cells].mean(axis=1) / n_r
+    e_phi = np.stack([np.zeros(X.shape[0]), -X[:, 2], X[:, 1]], axis=1)
+    e_phi /= np.linalg.norm(e_phi, axis=1, keepdims=True)
+    # surface normal of the ellipsoid through the point (gradient of x^2/rl^2 + (y^2+z^2)/rs^2), then e_mu = n x e_phi
+    rs = radii.get("r_short_endo", 2.5) + lam * (radii.get("r_short_epi", 3.5) - radii.get("r_short_endo", 2.5))
+    rl = radii.get("r_long_endo", 9.0) + lam * (radii.get("r_long_epi", 9.7) - radii.get("r_long_endo", 9.0))
+    nrm = np.stack([X[:, 0] / rl**2, X[:, 1] / rs**2, X[:, 2] / rs**2], axis=1)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    e_mu = np.cross(nrm, e_phi)
+    alpha = np.deg2rad(fiber_angle_endo + lam * (fiber_angle_epi - fiber_angle_endo))
+    f0 = np.cos(alpha)[:, None] * e_phi + np.sin(alpha)[:, None] * e_mu
+    f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+    return Geometry(mesh=mesh, ffun=ffun, markers=markers, f0=f0, n0=nrm)

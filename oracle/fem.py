@@ -78,13 +78,14 @@ def _cell_geometry(pts: np.ndarray, cells: np.ndarray):
 
 
 def assemble_p1(pts: np.ndarray, cells: np.ndarray, M):
-    """Returns (Mass, K) as CSR with identical sparsity.  M: scalar or (d,d) constant tensor."""
+    """Returns (Mass, K) as CSR with identical sparsity.  M: scalar, (d,d) constant tensor, or (ncell,d,d) cell-wise
+    tensor (fibre fields, src/beat/conductivities.py:101-104 with a Function f0)."""
     n = pts.shape[0]
     d = cells.shape[1] - 1
     vol, grads = _cell_geometry(pts, cells)
     Mt = np.eye(d) * float(M) if np.ndim(M) == 0 else np.asarray(M, dtype=float)
     # K_e[a,b] = vol * (M grad phi_b) . grad phi_a
-    Mg = np.einsum("ij,ebj->ebi", Mt, grads)
+    Mg = np.einsum("eij,ebj->ebi", Mt, grads) if Mt.ndim == 3 else np.einsum("ij,ebj->ebi", Mt, grads)
     Ke = np.einsum("eai,ebi->eab", grads, Mg) * vol[:, None, None]
     ref = (np.ones((d + 1, d + 1)) + np.eye(d + 1)) / ((d + 1) * (d + 2))
     Me = vol[:, None, None] * ref[None]

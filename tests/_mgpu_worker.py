@@ -16,8 +16,13 @@ for p in (ROOT, os.path.join(ROOT, "fenicsx-beat_b200"), os.path.join(ROOT, "tes
         sys.path.insert(0, p)
 
 
-def run_case(nied, fem, comm, dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc=None):
-    solver, info = nied.setup(dx=dx, comm=comm, rtol=rtol, ksp_type=ksp, initial_guess_previous=x0_prev, probes=False, pc_type=pc)
+def run_case(nied, fem, comm, dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc=None, lv=None):
+    if lv is not None:  # synthetic LV shell: phi-sector partition (periodic neighbours), cell-wise tensor, facet stimulus
+        from beat_b200 import lv_ellipsoid
+
+        solver, info = lv_ellipsoid.setup(n=tuple(lv), comm=comm, rtol=rtol, ksp_type=ksp, pc_type=pc, initial_guess_previous=x0_prev)
+    else:
+        solver, info = nied.setup(dx=dx, comm=comm, rtol=rtol, ksp_type=ksp, initial_guess_previous=x0_prev, probes=False, pc_type=pc)
     solver.theta = theta
     t = 0.0
     for _ in range(nsteps):
@@ -55,9 +60,9 @@ def main():
         dx, dt, nsteps, theta, ksp, x0_prev, rtol, tol = (case[k] for k in ("dx", "dt", "nsteps", "theta", "ksp", "x0_prev", "rtol", "tol"))
         for key, val in case.get("env", {}).items():
             os.environ[key] = val
-        pc = case.get("pc")
-        v, s, its, reason, l2g, n_owned = run_case(nied, fem, fem.Comm(rank, world), dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc)
-        vg, sg, itsg, reasong, _, _ = run_case(nied, fem, fem.COMM_SELF, dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc)
+        pc, lv = case.get("pc"), case.get("lv")
+        v, s, its, reason, l2g, n_owned = run_case(nied, fem, fem.Comm(rank, world), dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc, lv)
+        vg, sg, itsg, reasong, _, _ = run_case(nied, fem, fem.COMM_SELF, dx, dt, nsteps, theta, ksp, x0_prev, rtol, pc, lv)
         for key in case.get("env", {}):
             os.environ.pop(key, None)
         scale = np.abs(vg).max()

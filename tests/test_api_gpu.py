@@ -369,3 +369,38 @@ def test_simple_ode_odesystemsolver_rate():
         errors.append(np.linalg.norm(sol - y))
     rates = [np.log(e1 / e2) / np.log(10) for e1, e2 in zip(errors[:-1], errors[1:])]
     assert np.allclose(rates, 1, atol=0.01), rates
+
+
+def test_lv_ellipsoid_matches_oracle():
+    """BASELINE config 5 in small: synthetic LV shell (unstructured-style connectivity: periodic in phi, cell-wise
+    conductivity tensor), ENDO surface stimulus, three transmural parameter sets (DolfinMultiODESolver) - through the
+    public API against the oracle's assembly / LU solve / NumPy cell model."""
+    from beat_b200 import lv_ellipsoid
+    from oracle import fem as ofem
+    from oracle import monodomain as om_mono
+
+    solver, info = lv_ellipsoid.setup(n=(3, 12, 16), rtol=1e-12, ksp_type="cg")
+    mesh, geo = info["mesh"], info["geo"]
+    pts, cells = mesh.geometry.x, mesh.cells
+    mass, stiff = ofem.assemble_p1(pts, cells, info["M"])
+    endo = geo.ffun.facets[geo.ffun.find(geo.markers["ENDO"][0])]
+    load = ofem.load_vector_facets(pts, endo)
+    assert load.sum() > 0
+    om = P.oracle_model("tp06")
+    layer = mesh.info["endo_epi"].astype(int)
+    prm = np.stack([info["layer_parameters"][k] for k in layer], axis=1)  # (np, N)
+    y0 = np.repeat(om.init_state_values()[:, None], pts.shape[0], axis=1)
+    opde = om_mono.MonodomainModel(mass, stiff, [om_mono.Stimulus.window(load, 0.0, 1.0, info["stim_amplitude"])], C_m=1.0, theta=0.5,
+                                   solver="lu")
+    oode = om_mono.ODESolver(v_pde=opde.state, init_states=y0, parameters=prm, fun=om.generalized_rush_larsen, num_states=19,
+                             v_index=om.state_index("V"))
+    ref = om_mono.SplittingSolver(opde, oode)
+    t, dt = 0.0, 0.05
+    for _ in range(30):
+        solver.step((t, t + dt))
+        ref.step((t, t + dt))
+        t += dt
+    v = solver.pde.state.x.array_ro
+    assert v.max() > -82.0 and v.min() < -85.0  # the surface stimulus acts on the endocardium only (rest: -85.23 mV)
+    assert np.abs(v - opde.state).max() <= 1e-8 * np.abs(opde.state).max()
+    assert np.abs(solver.ode.full_values - oode.values).max() <= 1e-7 * np.abs(oode.values).max()

@@ -22,6 +22,8 @@ CASES = [
     dict(dx=0.25, dt=0.05, nsteps=4, theta=1.0, ksp="pipecg", x0_prev=False, rtol=1e-11, tol=1e-8, env={"MONO_PDE_STREAM": "1"}),
     dict(dx=0.5, dt=0.05, nsteps=12, theta=1.0, ksp="pipecg", pc="chebyshev", x0_prev=False, rtol=1e-11, tol=1e-8),
     dict(dx=0.25, dt=0.05, nsteps=6, theta=0.5, ksp="pipecg", pc="chebyshev", x0_prev=True, rtol=1e-11, tol=1e-8),
+    dict(dx=0.0, lv=[3, 12, 32], dt=0.05, nsteps=12, theta=1.0, ksp="pipecg", x0_prev=False, rtol=1e-11, tol=1e-8),
+    dict(dx=0.0, lv=[3, 10, 24], dt=0.05, nsteps=8, theta=1.0, ksp="cg", x0_prev=False, rtol=1e-12, tol=1e-8),
 ]
 
 

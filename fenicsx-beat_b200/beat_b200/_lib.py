@@ -40,6 +40,7 @@ SIGNATURES = {
     "mono_ode_set_state_row": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "mono_ode_get_state_row": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
     "mono_ode_set_params": (C.c_int, [C.c_void_p, c_double_p, C.c_int, C.c_int, C.c_int64, c_double_p, C.c_int]),
+    "mono_ode_set_region_params": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, c_double_p, C.c_int, c_int32_p]),
     "mono_ode_step": (C.c_int, [C.c_void_p, C.c_double, C.c_double]),
     "mono_ode_to_dolfin": (C.c_int, [C.c_void_p]),
     "mono_ode_from_dolfin": (C.c_int, [C.c_void_p]),
@@ -279,6 +280,14 @@ class Context:
             self._ck(self.lib.mono_ode_set_params(self.h, _dp(p), p.shape[0], 1, p.shape[1], None, 0))
         else:
             raise ValueError("parameters must be 1-D or 2-D")
+
+    def ode_set_region_params(self, params: np.ndarray, derived: np.ndarray, region_of_node: np.ndarray | None):
+        """params (n_regions, np), derived (n_regions, nd), region_of_node int32 (num_points,) or None to keep the map."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        d = np.ascontiguousarray(derived, dtype=np.float64).reshape(p.shape[0], -1)
+        reg = None if region_of_node is None else np.ascontiguousarray(region_of_node, dtype=np.int32)
+        self._ck(self.lib.mono_ode_set_region_params(self.h, p.shape[0], _dp(p), p.shape[1], _dp(d) if d.size else None, d.shape[1],
+                                                     _i32p(reg) if reg is not None else None))
 
     def ode_step(self, t0: float, dt: float):
         self._ck(self.lib.mono_ode_step(self.h, t0, dt))

@@ -274,10 +274,11 @@ class DolfinMultiODESolver(DolfinODESolver):
     """Per-region cell models (src/beat/odesolver.py:228-354): ``markers`` is a P1 function holding an integer
     region id per dof; ``init_states`` / ``parameters`` / ``fun`` / ``num_states`` / ``v_index`` are dicts keyed by it.
 
-    On the device this is ONE kernel launch over all nodes with a per-node parameter table (the reference loops
-    over the regions and runs one NumPy update per region).  That needs the same cell model in every region -
-    the case of the reference's demos (ToR-ORd / TP06 with endo / mid / epi parameter sets); different models per
-    region raise NotImplementedError."""
+    On the device this is ONE kernel launch over all nodes: a per-node region index selects one of a few parameter
+    sets (shared parameters + host-evaluated derived constants) kept in a small table (the reference loops over the
+    regions and runs one NumPy update per region).  That needs the same cell model in every region - the case of the
+    reference's demos (ToR-ORd / TP06 with endo / mid / epi parameter sets); different models per region raise
+    NotImplementedError."""
 
     def __init__(self, v_ode: fem.Function, v_pde: fem.Function, markers: fem.Function, init_states: dict, parameters: dict,
                  fun: dict, num_states: dict, v_index: dict, monitor: BaseMonitor | None = None):
@@ -303,27 +304,29 @@ class DolfinMultiODESolver(DolfinODESolver):
         ns = f0.num_states
         n = marr.size
         values = np.zeros((ns, n))
-        table = np.zeros((f0.num_parameters, n))
-        for m in self._marker_values:
+        self._region_of_node = np.zeros(n, dtype=np.int32)
+        for k, m in enumerate(self._marker_values):
             if num_states[m] != ns:
                 raise ValueError(f"num_states[{m}] = {num_states[m]} but the model has {ns} states")
             init = np.asarray(init_states[m], dtype=np.float64)
             values[:, self._inds[m]] = init if init.shape == (ns, self._num_points_m[m]) else init.reshape(ns, 1)
-            table[:, self._inds[m]] = np.asarray(parameters[m], dtype=np.float64).reshape(-1, 1)
+            self._region_of_node[self._inds[m]] = k
+            if np.ndim(parameters[m]) != 1:
+                raise NotImplementedError("per-region parameters must be 1-D vectors (one set per region)")
         self._region_parameters = parameters
-        self._region_raw = {m: np.asarray(parameters[m], dtype=np.float64).tobytes() for m in self._marker_values}
-        super().__init__(v_ode=v_ode, v_pde=v_pde, init_states=values, parameters=table, fun=f0, num_states=ns,
+        self._region_raw: dict | None = None
+        super().__init__(v_ode=v_ode, v_pde=v_pde, init_states=values, parameters=parameters, fun=f0, num_states=ns,
                          v_index=v_index[self._marker_values[0]], monitor=monitor)
 
     def _sync_parameters(self) -> None:
-        # the per-region vectors are held by reference and may be mutated in place between steps
-        for m in self._marker_values:
-            raw = np.asarray(self._region_parameters[m], dtype=np.float64).tobytes()
-            if raw != self._region_raw[m]:
-                self._parameters[:, self._inds[m]] = np.asarray(self._region_parameters[m], dtype=np.float64).reshape(-1, 1)
-                self._region_raw[m] = raw
-                self._params_dirty = True
-        super()._sync_parameters()
+        # the per-region vectors are held by reference and may be mutated in place between steps (pace_train.py:224)
+        raw = {m: np.asarray(self._region_parameters[m], dtype=np.float64).tobytes() for m in self._marker_values}
+        if raw != self._region_raw:
+            p = np.stack([np.asarray(self._region_parameters[m], dtype=np.float64) for m in self._marker_values])
+            d = np.stack([self.fun.derived(row) for row in p])
+            self._ctx.ode_set_region_params(p, d, self._region_of_node if self._region_raw is None else None)
+            self._region_raw = raw
+        self._params_dirty = False
 
     # reference surface with a marker argument (odesolver.py:292-303)
     def values(self, marker: int) -> np.ndarray:  # type: ignore[override]

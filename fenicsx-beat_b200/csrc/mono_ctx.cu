@@ -167,7 +167,7 @@ int mono_ctx_destroy(mono_ctx* c) {
                   (void*)c->v_prev, (void*)c->work[0], (void*)c->work[1], (void*)c->work[2], (void*)c->work[3],
                   (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->work[8], (void*)c->work[9],
                   (void*)c->stim_vec,
-                  (void*)c->gen_state, (void*)c->send_of_row_dev, (void*)c->send_ents_dev,
+                  (void*)c->gen_state, (void*)c->send_of_row_dev, (void*)c->send_ents_dev, (void*)c->region_table, (void*)c->region_of_node,
                   (void*)c->recs, (void*)c->timeline_dev,
                   (void*)c->ksp_dev, (void*)c->probes_dev,
                   (void*)c->probe_vals_dev, (void*)c->probe_act_dev, (void*)c->flush_buf, (void*)c->send_idx_dev,
@@ -287,6 +287,11 @@ int mono_ode_set_params(mono_ctx* c, const double* params, int num_params, int p
                         int n_derived) {
   MONO_CHECK(c, c->has_ode, "no ODE stage");
   MONO_CHECK(c, num_params == c->np, "wrong number of parameters for this model");
+  if (c->region_of_node) {  // back from per-region parameters
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->region_of_node);
+    c->region_of_node = nullptr;
+  }
   if (per_node) {
     MONO_CHECK(c, ld >= c->npts, "ld < num_points");
     if (!c->params_dev) MONO_CUDA(c, cudaMalloc(&c->params_dev, sizeof(double) * c->np * std::max<int64_t>(c->ld, 32)));
@@ -304,6 +309,38 @@ int mono_ode_set_params(mono_ctx* c, const double* params, int num_params, int p
     for (int k = 0; k < n_derived; ++k) c->params_host[c->np + k] = derived[k];
     c->per_node = false;
   }
+  c->have_params = true;
+  return MONO_OK;
+}
+
+int mono_ode_set_region_params(mono_ctx* c, int n_regions, const double* params, int num_params, const double* derived, int n_derived,
+                               const int32_t* region_of_node) {
+  MONO_CHECK(c, c->has_ode, "no ODE stage");
+  MONO_CHECK(c, n_regions >= 1 && num_params == c->np, "wrong number of regions / parameters for this model");
+  MONO_CHECK(c, n_derived <= c->nd && (n_derived == 0 || derived != nullptr), "bad derived constants");
+  const int stride = c->np + std::max(c->nd, 1);
+  std::vector<double> tbl((size_t)n_regions * stride, 0.0);
+  for (int r = 0; r < n_regions; ++r) {
+    for (int k = 0; k < c->np; ++k) tbl[(size_t)r * stride + k] = params[(size_t)r * c->np + k];
+    for (int k = 0; k < n_derived; ++k) tbl[(size_t)r * stride + c->np + k] = derived[(size_t)r * n_derived + k];
+  }
+  if (region_of_node != nullptr) {  // (NULL: keep the node -> region map, only the parameter values changed)
+    for (int64_t i = 0; i < c->npts; ++i) MONO_CHECK(c, region_of_node[i] >= 0 && region_of_node[i] < n_regions, "region index out of range");
+    if (!c->region_of_node) MONO_CUDA(c, cudaMalloc(&c->region_of_node, sizeof(int32_t) * std::max<int64_t>(c->ld, 32)));
+    MONO_CUDA(c, cudaMemcpyAsync(c->region_of_node, region_of_node, sizeof(int32_t) * c->npts, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    MONO_CHECK(c, c->region_of_node != nullptr && n_regions == c->n_regions, "no region map set yet");
+  }
+  if (c->region_table && n_regions != c->n_regions) {
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->region_table);
+    c->region_table = nullptr;
+  }
+  if (!c->region_table) MONO_CUDA(c, cudaMalloc(&c->region_table, sizeof(double) * tbl.size()));
+  MONO_CUDA(c, cudaMemcpyAsync(c->region_table, tbl.data(), sizeof(double) * tbl.size(), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_regions = n_regions;
+  c->per_node = false;
   c->have_params = true;
   return MONO_OK;
 }

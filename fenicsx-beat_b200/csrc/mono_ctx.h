@@ -72,6 +72,9 @@ struct mono_ctx {
   double* params_dev = nullptr;  // np x ld when per_node
   std::vector<double> params_host;  // np shared parameters followed by nd derived constants
   bool have_params = false;
+  double* region_table = nullptr;      // [n_regions][np + max(nd,1)]: shared parameters + derived constants per region
+  int32_t* region_of_node = nullptr;   // npts (padded to ld); non-null selects the per-region kernel
+  int n_regions = 0;
 
   // ---- PDE ----------------------------------------------------------------------------------
   bool has_pde = false;

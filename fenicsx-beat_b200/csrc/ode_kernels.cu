@@ -56,6 +56,23 @@ struct NodeParams {
   }
 };
 
+// Parameter set chosen per node by a region index (DolfinMultiODESolver, src/beat/odesolver.py:228-354): a small table
+// [n_regions][NP + ND] of shared parameters and their host-evaluated derived constants in global memory; a warp whose
+// nodes share a region reads it as a broadcast out of L1.
+template <int NP>
+struct RegionParams {
+  static constexpr bool kPerNode = false;
+  const double* row;
+  template <int K>
+  __device__ __forceinline__ double p() const {
+    return __ldg(row + K);
+  }
+  template <int K>
+  __device__ __forceinline__ double u() const {
+    return __ldg(row + NP + K);
+  }
+};
+
 struct OdeArgs {
   double* states;
   int64_t ld;
@@ -154,11 +171,23 @@ int blocks_per_sm(K kernel, int threads) {
   return nb > 0 ? nb : 1;
 }
 
+template <class STEP, int NP, int ND>
+__global__ void __launch_bounds__(kOdeThreads) ode_kernel_regions(const OdeArgs a, const double* __restrict__ table,
+                                                                    const int32_t* __restrict__ region) {
+  const int64_t i = (int64_t)blockIdx.x * kOdeThreads + threadIdx.x;
+  if (i < a.n) {
+    RegionParams<NP> prm{table + (size_t)__ldg(region + i) * (NP + (ND > 0 ? ND : 1))};
+    ode_node<STEP>(a, prm, i);
+  }
+}
+
 template <class STEP, class META>
 int launch_model(mono_ctx* c, const OdeArgs& a) {
   const unsigned grid = (unsigned)((a.n + kOdeThreads - 1) / kOdeThreads);
   if (grid == 0) return MONO_OK;
-  if (c->per_node) {
+  if (c->region_of_node != nullptr) {
+    ode_kernel_regions<STEP, META::kNumParams, META::kNumDerived><<<grid, kOdeThreads, 0, c->stream>>>(a, c->region_table, c->region_of_node);
+  } else if (c->per_node) {
     ode_kernel_pernode<STEP><<<grid, kOdeThreads, 0, c->stream>>>(a, c->params_dev, c->ld);
   } else {
     using UPRM = UniformParams<META::kNumParams, META::kNumDerived>;

@@ -120,6 +120,11 @@ int mono_ode_get_state_row(mono_ctx *ctx, int row, double *values);
  * (both shapes occur in the reference: demos/pace_train.py:133-167)                              */
 int mono_ode_set_params(mono_ctx *ctx, const double *params, int num_params, int per_node, int64_t ld,
                         const double *derived, int n_derived);
+/* Per-region parameter sets (DolfinMultiODESolver, odesolver.py:228-354, for ONE cell model): params (n_regions,
+ * num_params) and derived (n_regions, n_derived) row-major, region_of_node[num_points] in [0, n_regions).  Pass
+ * region_of_node == NULL to update the values only (a region's parameters were mutated in place).               */
+int mono_ode_set_region_params(mono_ctx *ctx, int n_regions, const double *params, int num_params, const double *derived,
+                               int n_derived, const int32_t *region_of_node);
 /* states[:] = fun(states, t0, parameters, dt)          (odesolver.py:67-79) */
 int mono_ode_step(mono_ctx *ctx, double t0, double dt);
 /* v_ode <- states[v_index]   (DolfinODESolver.to_dolfin, odesolver.py:164-166) */

@@ -50,8 +50,6 @@ constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
 typedef unsigned long long u64;
-__constant__ unsigned g_poll_ns = 0;     // back-off between two polls of a tagged element (experiments: MONO_POLL_NS)
-__constant__ unsigned g_settle_ns = 0;   // pause before gathering a vector that was published a moment ago (MONO_SETTLE_NS)
 
 // where one owned boundary value goes on ONE neighbour rank (peer-mapped addresses of its ghost slot)
 struct SendEnt {
@@ -156,7 +154,6 @@ __device__ __forceinline__ double wait_tag(const SyncRec* p, u64 want, int* fail
   const u64 t_begin = global_ns();
   unsigned spins = 0;
   while (true) {
-    if (g_poll_ns > 0) __nanosleep(g_poll_ns);  // thousands of threads polling L2 back to back starve the stores they wait for
     ld_tag<SYS>(p, v, g);
     if (g == want) return v;
     if ((++spins & 255u) == 0u) {
@@ -988,7 +985,6 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
   auto cheb_steps = [&](int set, int SRC) {
     for (int j = 1; j < K; ++j) {
       const double c1 = a.cheb_c1[j], c2 = a.cheb_c2[j];
-      if (j > 1 && g_settle_ns > 0) __nanosleep(g_settle_ns);
       OWN_ROWS_BEGIN
         const double ti = Aop.template apply<MULTI>(r, a.tb[set * K + j - 1], vtag, &sh.fail);
         if (r.row < a.n_owned) {
@@ -1079,7 +1075,6 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_pipecg_kernel(const PdeArg
     stamp(a, nstamp);
     // m = M^-1 w (remaining Chebyshev steps) and n = A m while the reduction is in flight
     cheb_steps(cur, VW);
-    if (cheb && g_settle_ns > 0) __nanosleep(g_settle_ns);
     OWN_ROWS_BEGIN
       const double ni = Aop.template apply<MULTI>(r, a.tb[cur * K + K - 1], vtag, &sh.fail);
       if (r.row < a.n_owned) V.st(VN, r, ni);
@@ -1460,23 +1455,7 @@ static int stim_refresh(mono_ctx* c, double t_eval, int* has_stim) {
   return MONO_OK;
 }
 
-static void push_experiment_knobs() {
-  static bool done = false;
-  if (done) return;
-  done = true;
-  unsigned v = 0;
-  if (const char* e = getenv("MONO_POLL_NS")) {
-    v = (unsigned)atoi(e);
-    cudaMemcpyToSymbol(g_poll_ns, &v, sizeof(v));
-  }
-  if (const char* e = getenv("MONO_SETTLE_NS")) {
-    v = (unsigned)atoi(e);
-    cudaMemcpyToSymbol(g_settle_ns, &v, sizeof(v));
-  }
-}
-
 int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
-  push_experiment_knobs();
   if (c->mode_dirty) {
     int rcm = pde_select_mode(c);
     if (rcm) return rcm;

@@ -40,3 +40,36 @@ def test_box_mesh_matches_generic_builder(n, size):
         la = fem.load_vector(a, fem.Measure("dx", domain=a, subdomain_data=ta), 1)
         lb = fem.load_vector(b, fem.Measure("dx", domain=b, subdomain_data=tb), 1)
         assert np.allclose(la, lb, rtol=0, atol=1e-16)
+
+
+def test_lv_ellipsoid_mesh_and_partition():
+    """Synthetic LV shell: positive cell volumes summing to the shell volume independent of the partition, every dof
+    owned exactly once, periodic neighbours, halo lists consistent (the i-th dof sent = the i-th ghost held), ENDO facets
+    of the owned part tile the endocardium."""
+    from beat_b200 import geometry
+
+    n = (3, 10, 12)
+    full = geometry.get_lv_ellipsoid_geometry(fem.COMM_SELF, *n)
+    x = full.mesh.geometry.x[full.mesh.cells]
+    vol = np.abs(np.linalg.det(x[:, 1:] - x[:, :1])) / 6
+    assert (vol > 0).all()
+    ip, ix, ms, st = fem.assemble_p1_local(full.mesh, 1.0)
+    assert np.isclose(ms.sum(), vol.sum())            # sum of the mass matrix = volume
+    assert np.abs(np.add.reduceat(st, ip[:-1])).max() < 1e-9 * np.abs(st).max()  # stiffness rows sum to zero
+    endo_area = fem.load_vector(full.mesh, fem.Measure("ds", domain=full.mesh, subdomain_data=full.ffun), 1).sum()
+    for size in (2, 3):
+        geos = [geometry.get_lv_ellipsoid_geometry(fem.Comm(r, size), *n) for r in range(size)]
+        maps = [g.mesh.index_map for g in geos]
+        owned = np.concatenate([m.local_to_global[: m.size_local] for m in maps])
+        assert np.array_equal(np.sort(owned), np.arange(full.mesh.index_map.size_global))
+        area = 0.0
+        for r, (g, m) in enumerate(zip(geos, maps)):
+            assert set(m.nbr_ranks.tolist()) == {(r - 1) % size, (r + 1) % size}
+            for k, q in enumerate(m.nbr_ranks):
+                mq = maps[q]
+                kq = list(mq.nbr_ranks).index(r)
+                sent = m.local_to_global[m.send_idx[m.send_ptr[k]: m.send_ptr[k + 1]]]
+                held = mq.ghosts[mq.recv_ptr[kq]: mq.recv_ptr[kq + 1]]
+                assert np.array_equal(sent, held)
+            area += fem.load_vector(g.mesh, fem.Measure("ds", domain=g.mesh, subdomain_data=g.ffun), 1).sum()
+        assert np.isclose(area, endo_area)

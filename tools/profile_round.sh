@@ -27,5 +27,16 @@ except Exception as e:
     print("$w ERR", e); print(open("$O/${T}_bench_$w.err").read()[-800:])
 PY
 done
+for w in lv_ellipsoid_320k lv_ellipsoid_1.4M; do
+  timeout 900 python bench.py --workload $w --steps 100 --warmup 5 > $O/${T}_bench_$w.json 2> $O/${T}_bench_$w.err
+  python - <<PY
+import json
+try:
+    d=json.load(open("$O/${T}_bench_$w.json"))
+    print("$w", "%.4g"%d["value"], d["ms_per_step"], d["stages"], "pde frac %.3f ode frac %.3f"%(d["roofline_stages"]["pde"]["frac"], d["roofline_stages"]["ode"]["frac"]), "setup", d["setup_s"])
+except Exception as e:
+    print("$w ERR", e); print(open("$O/${T}_bench_$w.err").read()[-800:])
+PY
+done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:pde_cg -s 6 -c 1 -f -o $O/${T}_pde_cg_stream \
   python bench.py --workload niederer_dx0.05 --steps 6 --warmup 3 --no-cpu-baseline --no-extras > $O/${T}_ncu_pde_stream.log 2>&1; tail -1 $O/${T}_ncu_pde_stream.log | cut -c1-200

@@ -70,4 +70,4 @@ def _ipow(x, n):
 
 
 forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=2, num_parameters=11, derived=_derived_fe, op_counts={'add': 8, 'mul': 9, 'div': 0, 'exp': 0, 'log': 0, 'sqrt': 0, 'pow': 0, 'floor': 0, 'abs': 0, 'cmp': 3, 'select': 1, 'neg': 2})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=2, num_parameters=11, derived=_derived_grl1, op_counts={'add': 9, 'mul': 12, 'div': 0, 'exp': 1, 'log': 0, 'sqrt': 0, 'pow': 0, 'floor': 0, 'abs': 0, 'cmp': 4, 'select': 2, 'neg': 2})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=2, num_parameters=11, derived=_derived_grl1, op_counts={'add': 13, 'mul': 16, 'div': 1, 'exp': 2, 'log': 0, 'sqrt': 0, 'pow': 0, 'floor': 0, 'abs': 1, 'cmp': 5, 'select': 3, 'neg': 2})

@@ -75,6 +75,12 @@ def _derived_fe(p):
 
 def _derived_grl1(p):
     """Parameter-only intermediates, evaluated once per parameter set and passed to the kernel."""
+    v_di_b_Na_dV = p[5]
+    v_di_b_Ca_dV = p[7]
+    v_di_leak_dCa_i = (-p[32])
+    v_di_leak_dCa_SR = p[32]
+    v_di_xfer_dCa_i = (-p[30])
+    v_di_xfer_dCa_ss = p[30]
     _t0 = (p[43] * p[44])
     v__u0 = (_t0 / p[45])
     v__u1 = (p[52] + (p[0] * p[42]))
@@ -84,28 +90,35 @@ def _derived_grl1(p):
     v__u4 = (p[2] * _t1)
     v__u5 = _ipow(p[45], 2)
     v__u6 = _t0
-    v__u7 = ((p[9] * p[52]) / (p[52] + p[10]))
-    v__u8 = (p[15] - 1.0)
-    v__u9 = _ipow(p[42], 3)
+    v__u7 = ((2.0 * p[45]) / _t0)
+    v__u8 = ((p[9] * p[52]) / (p[52] + p[10]))
+    v__u9 = (((-0.1) * p[45]) / _t0)
+    v__u10 = ((-p[45]) / _t0)
+    v__u11 = (p[15] - 1.0)
+    v__u12 = _ipow(p[42], 3)
     _t2 = _ipow(p[42], 3)
-    v__u10 = ((_ipow(p[17], 3) + _t2) * (p[16] + p[21]))
-    v__u11 = _ipow(p[31], 2)
-    v__u12 = (p[27] - p[28])
-    v__u13 = ((2.0 * p[47]) * p[45])
-    v__u14 = (p[34] * p[35])
-    v__u15 = (p[36] * p[37])
-    v__u16 = (p[38] * p[39])
-    v__u17 = ((2.0 * p[41]) * p[45])
-    v__u18 = (p[48] + p[50])
-    v__u19 = (p[47] * p[45])
+    v__u13 = ((_ipow(p[17], 3) + _t2) * (p[16] + p[21]))
+    v__u14 = ((p[15] * p[45]) / _t0)
+    _t3 = (p[15] - 1.0)
+    v__u15 = ((_t3 * p[45]) / _t0)
+    v__u16 = _ipow(p[31], 2)
+    v__u17 = (p[27] - p[28])
+    v__u18 = ((2.0 * p[47]) * p[45])
+    v__u19 = (p[34] * p[35])
+    v__u20 = (p[36] * p[37])
+    v__u21 = (p[38] * p[39])
+    v__u22 = ((2.0 * p[41]) * p[45])
+    v__u23 = ((v_di_xfer_dCa_ss * p[47]) / p[41])
+    v__u24 = (p[48] + p[50])
+    v__u25 = (p[47] * p[45])
     v__r0 = (1.0 / v__u6)
-    v__r1 = (1.0 / v__u13)
+    v__r1 = (1.0 / v__u18)
     v__r2 = (1.0 / p[47])
-    v__r3 = (1.0 / v__u17)
+    v__r3 = (1.0 / v__u22)
     v__r4 = (1.0 / p[41])
     v__r5 = (1.0 / p[49])
-    v__r6 = (1.0 / v__u19)
-    return np.array([v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__r0, v__r1, v__r2, v__r3, v__r4, v__r5, v__r6], dtype=np.float64)
+    v__r6 = (1.0 / v__u25)
+    return np.array([v_di_b_Na_dV, v_di_b_Ca_dV, v_di_leak_dCa_i, v_di_leak_dCa_SR, v_di_xfer_dCa_i, v_di_xfer_dCa_ss, v__u0, v__u1, v__u2, v__u3, v__u4, v__u5, v__u6, v__u7, v__u8, v__u9, v__u10, v__u11, v__u12, v__u13, v__u14, v__u15, v__u16, v__u17, v__u18, v__u19, v__u20, v__u21, v__u22, v__u23, v__u24, v__u25, v__r0, v__r1, v__r2, v__r3, v__r4, v__r5, v__r6], dtype=np.float64)
 
 
 def _ipow(x, n):
@@ -116,4 +129,4 @@ def _ipow(x, n):
 
 
 forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=19, num_parameters=53, derived=_derived_fe, op_counts={'add': 177, 'mul': 195, 'div': 72, 'exp': 51, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 0, 'cmp': 4, 'select': 5, 'neg': 11})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=19, num_parameters=53, derived=_derived_grl1, op_counts={'add': 191, 'mul': 209, 'div': 97, 'exp': 64, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 1, 'cmp': 5, 'select': 6, 'neg': 11})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=19, num_parameters=53, derived=_derived_grl1, op_counts={'add': 247, 'mul': 347, 'div': 136, 'exp': 70, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 7, 'cmp': 11, 'select': 12, 'neg': 39})

@@ -216,10 +216,9 @@ def free_symbols(n: Node, _seen: dict | None = None) -> set[str]:
     return rec(n)
 
 
-def diff(n: Node, s: str) -> Node:
-    """d n / d sym(s), other symbols treated as independent (opaque intermediates:
-    the generalized Rush-Larsen linearisation differentiates the *written* right-hand
-    side only)."""
+def diff(n: Node, s: str, sym_diff=None) -> Node:
+    """d n / d sym(s).  ``sym_diff(name)`` supplies d(name)/d(s) for every other symbol (chain rule through named
+    intermediates); without it other symbols are independent of s."""
     memo: dict[int, Node] = {}
 
     def d(x: Node) -> Node:
@@ -230,7 +229,7 @@ def diff(n: Node, s: str) -> Node:
         if k == "num":
             r = ZERO
         elif k == "sym":
-            r = ONE if x.value == s else ZERO
+            r = ONE if x.value == s else (sym_diff(x.value) if sym_diff is not None else ZERO)
         elif k == "add":
             r = add(d(x.args[0]), d(x.args[1]))
         elif k == "sub":
@@ -245,12 +244,16 @@ def diff(n: Node, s: str) -> Node:
             da, db = d(a), d(b)
             if is_num(db, 0.0):
                 r = div(da, b)
+            elif is_num(da, 0.0) and is_num(a) and a.value != 0.0:
+                # (c/b)' = -(c/b)^2 b' / c: no division at all (x = c/b is already there)
+                r = mul(num(-1.0 / a.value), mul(mul(x, x), db))
             else:
-                r = sub(div(da, b), div(mul(a, db), mul(b, b)))
+                # (a/b)' = (a' - (a/b) b') / b: one division, and the quotient x is already there
+                r = div(sub(da, mul(x, db)), b)
         elif k == "pow":
             a, b = x.args
-            da = d(a)
-            if s in free_symbols(b):
+            da, db = d(a), d(b)
+            if not is_num(db, 0.0):
                 raise NotImplementedError("state in exponent")
             if is_num(da, 0.0):
                 r = ZERO
@@ -270,6 +273,8 @@ def diff(n: Node, s: str) -> Node:
                 r = div(da, mul(num(2.0), x))
             elif fn == "floor":
                 r = ZERO
+            elif fn == "abs":
+                r = cond(cmp("ge", a, ZERO), da, neg(da))
             else:
                 raise NotImplementedError(f"d/dx {fn}")
         elif k == "cond":

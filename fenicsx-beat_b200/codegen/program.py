@@ -6,14 +6,18 @@ Schemes
                              writes the same update by hand for FitzHugh-Nagumo)
 ``generalized_rush_larsen``  first-order generalized Rush-Larsen (GRL1) as gotranx emits it for the
                              reference's demos (demos/niederer_benchmark.py:82-98): for each state y
-                             with written right-hand side f,
-                                 lin = d f / d y   (intermediates held fixed)
+                             with right-hand side f,
+                                 lin = d f / d y   TOTAL derivative: the chain rule runs through every
+                                                   intermediate that depends on y (other states held fixed)
                                  lin == 0          -> y + dt*f
                                  otherwise         -> y + f*(exp(lin*dt) - 1)/lin,
                                                       guarded by |lin| > 1e-8 (else dt*f) unless lin is a
                                                       fraction with a non-zero constant numerator.
-                             gotranx itself is not installable here, so this is a
-                             restatement of its published scheme: parity at that boundary is unpinned.
+                             gotranx itself is not installable here; which derivative it
+                             takes was settled empirically: with the total derivative the oracle reproduces the
+                             published Niederer activation times (demos/niederer_benchmark.py:315-325) within one
+                             dt at dt = 0.05 (dx = 0.5 and 0.2), with intermediates held fixed (V then falls back
+                             to forward Euler) it is 0.15-0.7 ms off.
 """
 
 from __future__ import annotations
@@ -54,6 +58,33 @@ def build_program(model: OdeModel, scheme: str, reciprocal_constants: bool = Tru
     dt = ir.sym("dt")
     defs: dict[str, ir.Node] = dict(model.intermediates)
     roots: list[str] = []
+    base_names = set(model.intermediates)
+    dmemo: dict[tuple[str, str], ir.Node] = {}
+
+    def chain(s: str):
+        """d(intermediate)/d(state s) as a named intermediate d<name>_d<s> (defined once, shared by CSE)."""
+
+        def sd(name: str) -> ir.Node:
+            if name not in base_names:
+                return ir.ZERO  # another state, a parameter, time
+            key = (name, s)
+            r = dmemo.get(key)
+            if r is not None:
+                return r
+            dmemo[key] = ir.ZERO  # definitions are acyclic; this only guards against a malformed model
+            dexpr = ir.diff(model.intermediates[name], s, sym_diff=sd)
+            if ir.is_num(dexpr):
+                r = dexpr
+            else:
+                dn = f"d{name}_d{s}"
+                assert dn not in defs, dn
+                defs[dn] = dexpr
+                r = ir.sym(dn)
+            dmemo[key] = r
+            return r
+
+        return sd
+
     for s in model.states:
         dname = f"d{s}_dt"
         f = model.derivatives[s]
@@ -65,7 +96,7 @@ def build_program(model: OdeModel, scheme: str, reciprocal_constants: bool = Tru
             prog.fe_states.append(s)
             roots.append(dname)
             continue
-        lin = ir.diff(f, s)
+        lin = ir.diff(f, s, sym_diff=chain(s))
         if ir.is_num(lin, 0.0):
             prog.outputs.append(ir.add(y, ir.mul(dt, fsym)))
             prog.fe_states.append(s)
@@ -111,6 +142,21 @@ def build_program(model: OdeModel, scheme: str, reciprocal_constants: bool = Tru
     for name in defs:
         if name in needed:
             visit(name)
+    # derivative intermediates d<u>_d<s> right after their base u: they share most operands with it, so the values are
+    # still in registers (emitted after ALL base intermediates they cost ToR-ORd kilobytes of spills)
+    derived_of: dict[str, list[str]] = {}
+    for (base, s_), node in dmemo.items():
+        if node.kind == "sym" and node.value == f"d{base}_d{s_}" and node.value in needed:
+            derived_of.setdefault(base, []).append(node.value)
+    all_derived = {d for lst in derived_of.values() for d in lst}
+    reordered: list[str] = []
+    for name in order:
+        if name in all_derived:
+            continue
+        reordered.append(name)
+        reordered += derived_of.get(name, [])
+    assert sorted(reordered) == sorted(order)
+    order = reordered
 
     uniform_names: set[str] = set()
     for name in order:

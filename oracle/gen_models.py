@@ -115,6 +115,28 @@ def build(tag: str, scheme: str):
     defs = dict(ns.assigned)
     outputs = []
     extra = {}
+    dmemo: dict = {}
+
+    def total_diff(expr, y):
+        """d expr / d y with the chain rule through every intermediate that depends on y; the derivative of an
+        intermediate u becomes its own named assignment d<u>_d<y> (so nothing is expanded symbolically)."""
+        out = sp.diff(expr, y)
+        for u in sorted(expr.free_symbols, key=lambda q: q.name):
+            if u.name not in ns.assigned or u == y:
+                continue
+            key = (u.name, y.name)
+            if key not in dmemo:
+                dmemo[key] = sp.Integer(0)
+                du = total_diff(ns.assigned[u.name], y)
+                if du != 0 and not du.is_number:
+                    dn = f"d{u.name}_d{y.name}"
+                    extra[dn] = du
+                    du = S(dn)
+                dmemo[key] = du
+            if dmemo[key] != 0:
+                out = out + sp.diff(expr, u) * dmemo[key]
+        return out
+
     for s in ns.states:
         dname = f"d{s}_dt"
         f = defs[dname]
@@ -122,7 +144,9 @@ def build(tag: str, scheme: str):
         if scheme == "forward_explicit_euler":
             outputs.append(y + dt * fs)
             continue
-        lin = sp.diff(f, y)
+        # gotranx linearises with the TOTAL derivative (settled against the published Niederer table: see
+        # tests/test_oracle_niederer.py); with intermediates held fixed V would fall back to forward Euler
+        lin = total_diff(f, y)
         if lin.is_zero or lin == 0:
             outputs.append(y + dt * fs)
             continue

@@ -271,7 +271,8 @@ def test_readme_unit_square_fhn():
 def test_niederer_full_config_activation_times():
     """BASELINE config 2 as the demo runs it (dx = 0.2 mm, dt = 0.01 ms, PETSc-default rtol): activation times from the
     device-side probes agree with the oracle's run of the same algorithm within one dt (north_star) - and, like the
-    oracle, with the published row (demos/niederer_benchmark.py:321) to the oracle's documented tolerance."""
+    oracle, with the published row (demos/niederer_benchmark.py:321) to 0.07 ms (0.2 %; the residual at small dt is the
+    reference's solver tolerance, tests/test_oracle_niederer.py)."""
     from beat_b200 import niederer
     from oracle import niederer as onied
 
@@ -285,7 +286,7 @@ def test_niederer_full_config_activation_times():
     for name, pid in info["probe_ids"].items():
         assert want[name] >= 0 and got[pid] >= 0, (name, want[name], got[pid])
         assert abs(got[pid] - want[name]) <= dt + 1e-9, (name, got[pid], want[name])
-        assert abs(got[pid] - pub[name]) <= 0.02 * pub[name] + dt, (name, got[pid], pub[name])
+        assert abs(got[pid] - pub[name]) <= 0.07, (name, got[pid], pub[name])  # ms; the oracle's own distance to the table at small dt
 
 
 # ---- the reference's splitting tests with its own two-state linear cell model, on the device -------------------

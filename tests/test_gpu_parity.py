@@ -45,7 +45,12 @@ def test_ode_single_step(ctx_factory, tag, scheme, n):
             want = getattr(om, scheme)(states, t0, 0.01, params)
         assert np.isfinite(got).all()
         err = rel_err(got, want, states)
-        assert err <= 1e-12, f"{tag}/{scheme} n={n} t={t0}: rel err {err:.3e}"
+        # Rush-Larsen increments f*(exp(lin*dt) - 1)/lin (gotranx writes exp(x) - 1, not expm1) cancel when |lin*dt| is
+        # small: two correctly rounded exp() that differ by one ulp then differ by ~ulp*|f/lin| in the state.  On 20 000
+        # random states per model that reaches ~2e-12 of the state's size (FitzHugh-Nagumo's cubic, the ToR-ORd membrane
+        # potential; more while a stimulus current is on); forward Euler and the golden vectors stay below 1e-12.
+        tol = 2e-11 if scheme == "generalized_rush_larsen" else 1e-12
+        assert err <= tol, f"{tag}/{scheme} n={n} t={t0}: rel err {err:.3e}"
     ctx.close()
 
 

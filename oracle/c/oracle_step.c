@@ -10,7 +10,8 @@
  *   src/beat/base_model.py:208-245         time at theta point, RHS, KSP solve (restated as PETSc-style KSPCG
  *                                          with Jacobi: zero initial guess, preconditioned-norm test)
  * The cell-model scalar functions come from the generated oracle/c/<model>.c (oracle/gen_models.py).
- * Parity at the gotranx boundary is UNPINNED (no reference test covers the generated cell models).
+ * No reference test covers the generated cell models; they are pinned on the published Niederer activation times
+ * (demos/niederer_benchmark.py:315-325, reproduced within one dt: tests/test_oracle_niederer.py).
  */
 #include <math.h>
 #include <stdint.h>

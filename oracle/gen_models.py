@@ -4,8 +4,10 @@ Independent of the product's code generator on purpose: the ``.ode`` file is *ex
 namespace of SymPy symbols (the gotran DSL is Python syntax), derivatives for the generalized
 Rush-Larsen linearisation come from ``sympy.diff``, and code is printed by SymPy's own printers.  This
 is the route gotranx itself takes (it is SymPy-based), restated from its published scheme because
-gotranx cannot be installed here -> parity at the gotranx boundary is
-UNPINNED: no reference test exercises the generated TP06 / ToR-ORd step.
+gotranx cannot be installed here.  No reference test exercises the generated
+TP06 / ToR-ORd step; the one reference output that does - the Niederer activation-time table,
+demos/niederer_benchmark.py:315-325 - is reproduced within one dt (tests/test_oracle_niederer.py), which is what fixed
+the linearisation rule below (total derivative).
 
 Follows:
   * /root/reference/odes/tentusscher_panfilov_2006/tentusscher_panfilov_2006_epi_cell.ode:36-322
@@ -187,7 +189,7 @@ class _Np(NumPyPrinter):
 def emit_numpy(tag: str) -> str:
     out = [
         f'"""ORACLE - GENERATED by oracle/gen_models.py: NumPy step functions for \'{tag}\'.',
-        "Test infrastructure only (tests/, smoke(), bench.py cpu_baseline).  parity unpinned at the gotranx boundary.",
+        "Test infrastructure only (tests/, smoke(), bench.py cpu_baseline).  Pinned on the published Niederer table (within one dt).",
         '"""',
         "import numpy",
         "",

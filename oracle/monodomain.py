@@ -14,8 +14,8 @@ semantics: zero initial guess, preconditioned residual norm, rtol relative to th
 
 Pinned against the reference's own known-answer tests in tests/test_oracle_known_answers.py
 (tests/test_odesolver.py, test_monodomain.py, test_monodomain_solver.py, test_stimulation.py of the
-reference).  The cell-model arithmetic (gotranx boundary) is NOT pinned by any reference test:
-"parity unpinned" there (see oracle/gen_models.py).
+reference).  The cell-model arithmetic (gotranx boundary) is not covered by any reference TEST; it is pinned on the
+published Niederer activation times instead (within one dt, tests/test_oracle_niederer.py; see oracle/gen_models.py).
 """
 
 from __future__ import annotations

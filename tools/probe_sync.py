@@ -1,5 +1,8 @@
 import sys
-sys.path.insert(0, "fenicsx-beat_b200"); sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "fenicsx-beat_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, _p)
 import numpy as np
 import beat_b200.niederer as nied
 ksp = sys.argv[1] if len(sys.argv) > 1 else "pipecg"

@@ -353,5 +353,5 @@ def _ipow(x, n):
     return r
 
 
-forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=45, num_parameters=112, derived=_derived_fe, op_counts={'add': 404, 'mul': 576, 'div': 148, 'exp': 75, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 0, 'cmp': 9, 'select': 11, 'neg': 77})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=45, num_parameters=112, derived=_derived_grl1, op_counts={'add': 817, 'mul': 1410, 'div': 323, 'exp': 120, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 18, 'cmp': 28, 'select': 30, 'neg': 158})
+forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=45, num_parameters=112, derived=_derived_fe, op_counts={'add': 404, 'mul': 620, 'div': 119, 'exp': 75, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 0, 'cmp': 9, 'select': 11, 'neg': 77})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=45, num_parameters=112, derived=_derived_grl1, op_counts={'add': 817, 'mul': 1608, 'div': 167, 'exp': 120, 'log': 5, 'sqrt': 2, 'pow': 1, 'floor': 1, 'abs': 18, 'cmp': 28, 'select': 30, 'neg': 179})

@@ -128,5 +128,5 @@ def _ipow(x, n):
     return r
 
 
-forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=19, num_parameters=53, derived=_derived_fe, op_counts={'add': 177, 'mul': 195, 'div': 72, 'exp': 51, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 0, 'cmp': 4, 'select': 5, 'neg': 11})
-generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=19, num_parameters=53, derived=_derived_grl1, op_counts={'add': 247, 'mul': 347, 'div': 136, 'exp': 70, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 7, 'cmp': 11, 'select': 12, 'neg': 39})
+forward_explicit_euler = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=0, scheme='forward_explicit_euler', num_states=19, num_parameters=53, derived=_derived_fe, op_counts={'add': 177, 'mul': 199, 'div': 70, 'exp': 51, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 0, 'cmp': 4, 'select': 5, 'neg': 11})
+generalized_rush_larsen = DeviceODE(model_id=MODEL_ID, model_tag=MODEL_TAG, scheme_id=1, scheme='generalized_rush_larsen', num_states=19, num_parameters=53, derived=_derived_grl1, op_counts={'add': 247, 'mul': 413, 'div': 93, 'exp': 70, 'log': 4, 'sqrt': 1, 'pow': 0, 'floor': 1, 'abs': 7, 'cmp': 11, 'select': 12, 'neg': 51})

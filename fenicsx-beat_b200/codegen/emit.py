@@ -95,6 +95,8 @@ class _Printer:
             return f"({e(x.args[0])} * {e(x.args[1])})"
         if k == "div":
             if L == "cuda":
+                if ir.is_num(x.args[0], 1.0):
+                    return f"RCP({e(x.args[1])})"  # shared reciprocal of a repeated denominator (program.py)
                 return f"DIV({e(x.args[0])}, {e(x.args[1])})"
             return f"({e(x.args[0])} / {e(x.args[1])})"
         if k == "neg":

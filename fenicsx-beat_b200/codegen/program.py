@@ -195,7 +195,52 @@ def build_program(model: OdeModel, scheme: str, reciprocal_constants: bool = Tru
     prog.outputs = [ir.rebuild(e, leaf_map, memo) for e in prog.outputs]
     if reciprocal_constants:
         _divisions_by_constants_to_multiplications(prog, params, uniform_names)
+        _shared_denominators_to_reciprocals(prog)
     return prog
+
+
+def _shared_denominators_to_reciprocals(prog: Program) -> None:
+    """a/b, c/b, ... with the SAME node-dependent denominator b  ->  r = 1/b once, then a*r, c*r, ...  The total-
+    derivative Rush-Larsen rule produces many of these (f = (y_inf - y)/tau with lin = -1/tau; the quotient rule divides
+    by the denominator of the quotient it differentiates): 78 of TP06's 136 divisions share 35 denominators.  On the
+    device a reciprocal is a seed + two Newton steps (RCP, csrc/ode_math.cuh), so a group of n divisions costs 6 + n
+    instructions instead of 8 n.  Each product is within 1.5 ulp of the quotient.  DEVICE code only."""
+    seen: set[int] = set()
+    uses: dict[int, int] = {}
+
+    def count(x: ir.Node) -> None:
+        if id(x) in seen:
+            return
+        seen.add(id(x))
+        for a in x.args:
+            count(a)
+        if x.kind == "div" and not ir.is_num(x.args[1]) and not ir.is_num(x.args[0], 1.0):
+            uses[id(x.args[1])] = uses.get(id(x.args[1]), 0) + 1
+
+    for _, e in prog.body:
+        count(e)
+    for e in prog.outputs:
+        count(e)
+    shared = {k for k, n in uses.items() if n >= 2}
+    memo: dict[int, ir.Node] = {}
+
+    def rec(x: ir.Node) -> ir.Node:
+        r = memo.get(id(x))
+        if r is not None:
+            return r
+        if not x.args:
+            r = x
+        else:
+            old_den = x.args[1] if x.kind == "div" else None
+            a = tuple(rec(c) for c in x.args)
+            r = x if all(p is q for p, q in zip(a, x.args)) else ir._mk(x.kind, a, x.value)
+            if old_den is not None and id(old_den) in shared and not ir.is_num(a[0], 1.0):
+                r = ir.mul(a[0], ir.div(ir.ONE, a[1]))  # div(ONE, b) is hash-consed: one reciprocal per denominator
+        memo[id(x)] = r
+        return r
+
+    prog.body = [(n, rec(e)) for n, e in prog.body]
+    prog.outputs = [rec(e) for e in prog.outputs]
 
 
 def _divisions_by_constants_to_multiplications(prog: Program, params: set, uniform_names: set) -> None:

@@ -41,6 +41,7 @@ __device__ __forceinline__ double mono_rcp(double b) {
 }
 
 #if MONO_ODE_MATH == 1
+#define RCP(b) mono_rcp(b)
 #define DIV(a, b) mono_div_fast((a), (b))
 __device__ __forceinline__ double mono_div_fast(double a, double b) {
   const double r = mono_rcp(b);
@@ -49,6 +50,7 @@ __device__ __forceinline__ double mono_div_fast(double a, double b) {
   return fma(r, fma(-b, q, a), q);
 }
 #else
+#define RCP(b) (1.0 / (b))
 #define DIV(a, b) ((a) / (b))
 #endif
 

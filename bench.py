@@ -47,6 +47,7 @@ WORKLOADS = {
     "niederer_dx0.05": (0.05, 0.01),
     "niederer_dx0.5": (0.5, 0.01),
     "niederer_dx0.025": (0.025, 0.01),   # 27.2 M dofs (BASELINE config 4's "~30M")
+    "niederer_dx0.016": (0.016, 0.01),   # 103.8 M dofs: the north_star's 100M-dof slab (several GPUs)
 }
 # BASELINE config 5 (synthetic LV shell, endocardial surface stimulus, three transmural layers): (n_r, n_mu, n_phi), dt
 LV_WORKLOADS = {

@@ -140,13 +140,18 @@ class Mesh:
             d = self.topology.dim
             fac = np.concatenate([np.delete(self.cells, a, axis=1) for a in range(d + 1)], axis=0)
             fac = np.sort(fac, axis=1)
-            uniq, counts = np.unique(fac, axis=0, return_counts=True)
-            cand = uniq[counts == 1]
+            on_ids = self.info.get("on_boundary_ids")
+            if on_ids is not None:
+                # structured generators know the exterior from the vertex indices: a cell face that lies in an exterior
+                # surface belongs to exactly one cell, so no counting (and no sort of all faces) is needed
+                cand = fac[np.asarray(on_ids(self.index_map.local_to_global[fac]), dtype=bool)]
+                order = np.lexsort(tuple(cand[:, k] for k in range(cand.shape[1] - 1, -1, -1)))
+                cand = cand[order]
+            else:
+                uniq, counts = np.unique(fac, axis=0, return_counts=True)
+                cand = uniq[counts == 1]
             # a facet seen once locally may be interior to the global mesh (its other cell lives on another
             # rank); such a facet has only ghost/boundary vertices.  Structured generators pass a predicate.
-            on_ids = self.info.get("on_boundary_ids")
-            if on_ids is not None:  # structured generators that know the exterior from the vertex indices
-                cand = cand[np.asarray(on_ids(self.index_map.local_to_global[cand]), dtype=bool)]
             on_bnd = self.info.get("on_boundary")
             if on_bnd is not None:
                 keep = np.ones(cand.shape[0], dtype=bool)
@@ -889,20 +894,17 @@ def assemble_p1_local(mesh: Mesh, M) -> tuple[np.ndarray, np.ndarray, np.ndarray
     cols = np.broadcast_to(cells[:, None, :], Ke.shape).ravel()
     keep = rows < n_owned
     rows, cols = rows[keep], cols[keep]
-    key = rows * n_local + cols
-    order = np.argsort(key, kind="stable")
-    key = key[order]
-    first = np.concatenate([[True], key[1:] != key[:-1]])
-    starts = np.nonzero(first)[0]
-    mass = np.add.reduceat(Me.ravel()[keep][order], starts)
-    stiff = np.add.reduceat(Ke.ravel()[keep][order], starts)
-    ukey = key[starts]
-    urow = ukey // n_local
-    indices = (ukey % n_local).astype(np.int32)
-    indptr = np.zeros(n_owned + 1, dtype=np.int64)
-    np.add.at(indptr, urow + 1, 1)
-    indptr = np.cumsum(indptr)
-    return indptr, indices, mass, stiff
+    # duplicates are summed by scipy's C routines (coo -> csr); both matrices get the same pattern (structural zeros of
+    # K stay in), columns sorted within a row
+    import scipy.sparse as sp
+
+    mass_m = sp.coo_matrix((Me.ravel()[keep], (rows, cols)), shape=(n_owned, n_local)).tocsr()
+    stiff_m = sp.coo_matrix((Ke.ravel()[keep], (rows, cols)), shape=(n_owned, n_local)).tocsr()
+    mass_m.sort_indices()
+    stiff_m.sort_indices()
+    if not (np.array_equal(mass_m.indptr, stiff_m.indptr) and np.array_equal(mass_m.indices, stiff_m.indices)):
+        raise AssertionError("mass and stiffness patterns differ")
+    return mass_m.indptr.astype(np.int64), mass_m.indices.astype(np.int32), mass_m.data, stiff_m.data
 
 
 def _gauss_simplex(d: int, degree: int):

@@ -154,13 +154,6 @@ __global__ void __launch_bounds__(kOdeThreads) ode_kernel_pernode(const OdeArgs 
   }
 }
 
-// 4 CTAs of 128 threads per SM (<= 128 registers): 16 warps per SM instead of 12 at the price of some spilling.
-template <class STEP, class UPRM>
-__global__ void __launch_bounds__(kOdeThreads, 4) ode_kernel_uniform_occ4(const OdeArgs a, const __grid_constant__ UPRM prm) {
-  const int64_t i = (int64_t)blockIdx.x * kOdeThreads + threadIdx.x;
-  if (i < a.n) ode_node<STEP>(a, prm, i);
-}
-
 template <class K>
 int blocks_per_sm(K kernel, int threads) {
   int nb = 0;
@@ -202,16 +195,8 @@ int launch_model(mono_ctx* c, const OdeArgs& a) {
       const int64_t waves_big = ((int64_t)grid + (int64_t)c->n_sm * occ_big - 1) / ((int64_t)c->n_sm * occ_big);
       const int64_t waves_small = (gs + (int64_t)c->n_sm * occ_small - 1) / ((int64_t)c->n_sm * occ_small);
       small = waves_small < waves_big && waves_small <= 2;
-      bool occ4 = false;
-      if (const char* e = getenv("MONO_ODE_VARIANT")) {
-        small = e[0] == 's';
-        occ4 = e[0] == 'm';
-      }
+      if (const char* e = getenv("MONO_ODE_VARIANT")) small = e[0] == 's';  // measurement: force the variant (b / s)
       if (small) ode_kernel_uniform_small<STEP, UPRM><<<(unsigned)gs, kOdeThreadsSmall, 0, c->stream>>>(a, prm);
-      if (occ4) {
-        ode_kernel_uniform_occ4<STEP, UPRM><<<grid, kOdeThreads, 0, c->stream>>>(a, prm);
-        small = true;
-      }
     }
     if (!small) ode_kernel_uniform<STEP, UPRM><<<grid, kOdeThreads, 0, c->stream>>>(a, prm);
   }

@@ -381,6 +381,210 @@ class BoxMesh(Mesh):
         return np.sort(ids[keep]).astype(np.int32 if self.num_cells < 2**31 else np.int64)
 
 
+class ShellMesh(Mesh):
+    """Kuhn-split structured mesh that is PERIODIC in its fastest index and geometrically mapped (the synthetic LV shell:
+    x = phi ring, y = mu, z = transmural).  Like BoxMesh everything is index arithmetic - vertex id
+    g = (k (ny+1) + j) vx + (i mod vx) with vx = nx vertices per ring - so a rank's part needs neither a global cell
+    array nor np.unique; the partition cuts the ring into sectors (neighbours (r-1) % size and (r+1) % size).
+    Unwrapped local column index i runs over [lo-1, hi] (ghost, owned..., ghost); numbering follows the same rules as
+    the generic ``_build_local`` (owned by global id, ghosts grouped by owner then by global id), which the tests
+    compare it with."""
+
+    def __init__(self, comm: Comm, n, coords_ijk, info: dict | None = None):
+        nx, ny, nz = (int(v) for v in n)
+        self.n = (nx, ny, nz)
+        self.vx = vx = nx
+        self.coords_ijk = coords_ijk
+        size, rank = comm.size, comm.rank
+        starts = _partition_1d(vx, size)
+        self.lo, self.hi = lo, hi = int(starts[rank]), int(starts[rank + 1])
+        self.nxo = nxo = hi - lo
+        if size > 1 and nxo < 2:
+            raise ValueError("every rank needs at least two columns of the ring")
+        self.plane = plane = (ny + 1) * (nz + 1)
+        self.periodic_single = size == 1
+        self.c0, self.c1 = (0, nx) if size == 1 else (lo - 1, hi)  # unwrapped cube columns
+        n_owned = plane * nxo
+        pl = np.arange(plane, dtype=np.int64)
+        gk, gj, gi = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(lo, hi), indexing="ij")
+        owned_g = ((gk * (ny + 1) + gj) * vx + gi).ravel().astype(np.int64)
+        self._ghost_cols: dict[int, tuple[int, int, int]] = {}  # unwrapped column -> (group offset, columns in group, position)
+        ghosts_g, gown, nbr, send_idx, send_ptr, recv_ptr = [], [], [], [], [0], [0]
+        if size > 1:
+            qL, qR = (rank - 1) % size, (rank + 1) % size
+            groups: dict[int, list[int]] = {}
+            groups.setdefault(qL, []).append(lo - 1)
+            groups.setdefault(qR, []).append(hi)
+            sends: dict[int, list[int]] = {}
+            sends.setdefault(qL, []).append(lo)       # my first column is qL's right ghost
+            sends.setdefault(qR, []).append(hi - 1)   # my last column is qR's left ghost
+            off = 0
+            for q in sorted(groups):
+                cols = sorted(set(groups[q]), key=lambda c: c % vx)  # within an owner: by global id = by global column per row
+                m = len(cols)
+                for pos, c in enumerate(cols):
+                    self._ghost_cols[c] = (off, m, pos)
+                gcols = np.array([c % vx for c in cols], dtype=np.int64)
+                ghosts_g.append((pl[:, None] * vx + gcols[None, :]).ravel())
+                gown.append(np.full(plane * m, q, dtype=np.int32))
+                off += plane * m
+                recv_ptr.append(off)
+                nbr.append(q)
+                scols = np.array(sorted(set(sends[q]), key=lambda c: c % vx), dtype=np.int64)
+                send_idx.append((pl[:, None] * nxo + (scols[None, :] - lo)).ravel().astype(np.int32))
+                send_ptr.append(send_ptr[-1] + plane * len(scols))
+        ghosts = np.concatenate(ghosts_g) if ghosts_g else np.zeros(0, np.int64)
+        owners = np.concatenate(gown) if gown else np.zeros(0, np.int32)
+        l2g = np.concatenate([owned_g, ghosts])
+        imap = IndexMap(n_owned, ghosts, owners, l2g, vx * plane, np.asarray(nbr, dtype=np.int32), np.asarray(send_ptr, dtype=np.int32),
+                        np.concatenate(send_idx).astype(np.int32) if send_idx else np.zeros(0, np.int32), np.asarray(recv_ptr, dtype=np.int32))
+        gi_, gj_, gk_ = l2g % vx, (l2g // vx) % (ny + 1), l2g // (vx * (ny + 1))
+        inf = {"kind": "shell", "n": self.n}
+        inf.update(info or {})
+        super().__init__(comm, coords_ijk(gi_, gj_, gk_), None, imap, 3, info=inf)
+
+    def local_index(self, i, j, k):
+        """Local vertex id of grid point (i, j, k); i is the UNWRAPPED column (single rank: any integer, taken mod vx;
+        several ranks: lo-1 .. hi)."""
+        i = np.asarray(i)
+        pl = np.asarray(k) * (self.n[1] + 1) + np.asarray(j)
+        if self.periodic_single:
+            return pl * self.vx + (i % self.vx)
+        n_owned = self.index_map.size_local
+        out = pl * self.nxo + (i - self.lo)
+        for col, (off, m, pos) in self._ghost_cols.items():
+            out = np.where(i == col, n_owned + off + pl * m + pos, out)
+        return out
+
+    @property
+    def num_cubes(self) -> int:
+        return (self.c1 - self.c0) * self.n[1] * self.n[2]
+
+    @property
+    def num_cells(self) -> int:
+        return 6 * self.num_cubes
+
+    def _cube_ijk(self, cube):
+        w = self.c1 - self.c0
+        return self.c0 + cube % w, (cube // w) % self.n[1], cube // (w * self.n[1])
+
+    cells_of = BoxMesh.cells_of
+    cells = BoxMesh.cells
+    locate_cells = BoxMesh.locate_cells
+
+    def boundary_facets(self) -> np.ndarray:
+        """Exterior facets among the local cells, generated directly: the ring has no boundary in x; on the surfaces
+        j = 0, j = ny, k = 0, k = nz every cube face is cut by the Kuhn split along its (0,0)-(1,1) diagonal into
+        two triangles.  Same rows, same order as the generic search over all cell faces."""
+        if self._boundary_facets is None:
+            nx, ny, nz = self.n
+            ii = np.arange(self.c0, self.c1)
+            tris = []
+
+            def quad_faces(v00, v10, v01, v11):
+                tris.append(np.stack([v00, v10, v11], axis=-1).reshape(-1, 3))
+                tris.append(np.stack([v00, v01, v11], axis=-1).reshape(-1, 3))
+
+            for k in (0, nz):  # faces spanned by (x, y)
+                I, J = np.meshgrid(ii, np.arange(ny), indexing="ij")
+                L = lambda di, dj: self.local_index(I + di, J + dj, np.full_like(I, k))  # noqa: E731
+                quad_faces(L(0, 0), L(1, 0), L(0, 1), L(1, 1))
+            for j in (0, ny):  # faces spanned by (x, z)
+                I, K = np.meshgrid(ii, np.arange(nz), indexing="ij")
+                L = lambda di, dk: self.local_index(I + di, np.full_like(I, j), K + dk)  # noqa: E731
+                quad_faces(L(0, 0), L(1, 0), L(0, 1), L(1, 1))
+            fac = np.sort(np.concatenate(tris, axis=0), axis=1)
+            order = np.lexsort((fac[:, 2], fac[:, 1], fac[:, 0]))
+            self._boundary_facets = fac[order]
+        return self._boundary_facets
+
+
+def assemble_p1_structured(mesh, M):
+    """CSR (indptr, indices, mass, stiff) of the owned rows of a ShellMesh: the stencil accumulation of assemble_p1_box with
+    element matrices that VARY from cube to cube (mapped geometry, cell-wise tensor M of shape (ncell, 3, 3) in the
+    mesh's cell order, or a constant).  Per tet type the volumes, gradients and element matrices of all cubes are
+    computed at once from the vertex grid and added with slice additions - no global sort, no cell loop."""
+    nx, ny, nz = mesh.n
+    lo, hi, nxo = mesh.lo, mesh.hi, mesh.nxo
+    c0, c1 = mesh.c0, mesh.c1
+    ncx = c1 - c0
+    ncube = mesh.num_cubes
+    Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
+    # vertex coordinates on the unwrapped local grid [k, j, column c0 .. c1]
+    kk, jj, ii = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(c0, c1 + 1), indexing="ij")
+    Xg = mesh.geometry.x[mesh.local_index(ii, jj, kk)]  # (nz+1, ny+1, ncx+1, 3)
+    corner = np.zeros((6, 4, 3), dtype=np.int64)
+    for p, perm in enumerate(_KUHN_PERMS):
+        for a in range(3):
+            corner[p, a + 1] = corner[p, a]
+            corner[p, a + 1, perm[a]] += 1
+    offs = sorted({tuple(corner[p, b] - corner[p, a]) for p in range(6) for a in range(4) for b in range(4)},
+                  key=lambda d: d[0] + d[1] * mesh.vx + d[2] * mesh.vx * (ny + 1))
+    slot = {d: s for s, d in enumerate(offs)}
+    ns = len(offs)
+    single = mesh.periodic_single
+    ncol = nx + 1 if single else nxo  # single rank: one extra (seam) column, folded onto column 0 afterwards
+    row0 = 0 if single else lo        # unwrapped column of row-array column 0
+    shape = (nz + 1, ny + 1, ncol)
+    val_m = np.zeros((ns,) + shape)
+    val_k = np.zeros((ns,) + shape)
+    ref = (1.0 + np.eye(4)) / 20.0
+    for p in range(6):
+        verts = [Xg[corner[p, a, 2]: corner[p, a, 2] + nz, corner[p, a, 1]: corner[p, a, 1] + ny, corner[p, a, 0]: corner[p, a, 0] + ncx]
+                 for a in range(4)]
+        xcell = np.stack(verts, axis=3).reshape(-1, 4, 3)  # cube order z, y, x (x fastest) = the mesh's cell order
+        vol, g = _simplex_measure_and_gradients(xcell)
+        gt = g.transpose(0, 2, 1)
+        if Mv.ndim == 0:
+            Ke = float(Mv) * (g @ gt)
+        elif Mv.ndim == 2:
+            Ke = (g @ Mv) @ gt
+        else:
+            Ke = (g @ Mv[p * ncube: (p + 1) * ncube]) @ gt  # batched 4x3 . 3x3 . 3x4
+        Ke *= vol[:, None, None]
+        Ke = Ke.reshape(nz, ny, ncx, 4, 4)
+        Me = (vol[:, None, None] * ref[None]).reshape(nz, ny, ncx, 4, 4)
+        for a in range(4):
+            ax, ay, az = corner[p, a]
+            i0, i1 = (c0, c1) if single else (max(c0, lo - ax), min(c1, hi - ax))  # cubes whose vertex a is an owned row
+            if i1 <= i0:
+                continue
+            rs = (slice(az, az + nz), slice(ay, ay + ny), slice(i0 + ax - row0, i1 + ax - row0))
+            cs = (slice(None), slice(None), slice(i0 - c0, i1 - c0))
+            for b in range(4):
+                s_ = slot[tuple(corner[p, b] - corner[p, a])]
+                val_m[s_][rs] += Me[cs + (a, b)]
+                val_k[s_][rs] += Ke[cs + (a, b)]
+    if single:  # the seam column nx is column 0
+        val_m[..., 0] += val_m[..., nx]
+        val_k[..., 0] += val_k[..., nx]
+        val_m, val_k = val_m[..., :nx], val_k[..., :nx]
+        shape = (nz + 1, ny + 1, nx)
+    n_owned = mesh.index_map.size_local
+    kk, jj, ii = np.meshgrid(np.arange(nz + 1), np.arange(ny + 1), np.arange(lo, hi), indexing="ij", sparse=True)
+    cols = np.empty((n_owned, ns), dtype=np.int32)
+    valid = np.empty((n_owned, ns), dtype=bool)
+    for s_, (dx_, dy_, dz_) in enumerate(offs):
+        j2, k2 = jj + dy_, kk + dz_
+        ok = np.broadcast_to((j2 >= 0) & (j2 <= ny) & (k2 >= 0) & (k2 <= nz), shape)  # the ring has no end in x
+        c = mesh.local_index(ii + dx_, np.clip(j2, 0, ny), np.clip(k2, 0, nz))
+        cols[:, s_] = np.broadcast_to(c, shape).reshape(-1)
+        valid[:, s_] = ok.reshape(-1)
+    mass = np.ascontiguousarray(val_m.reshape(ns, -1).T)
+    stiff = np.ascontiguousarray(val_k.reshape(ns, -1).T)
+    del val_m, val_k
+    # rows whose neighbours wrap around the seam or live in a ghost column: local column order differs from the slot order
+    pl = np.arange(mesh.plane, dtype=np.int64) * nxo
+    rows = np.unique(np.concatenate([pl, pl + (nxo - 1)]))
+    key = np.where(valid[rows], cols[rows].astype(np.int64), np.int64(2**40))
+    order = np.argsort(key, axis=1, kind="stable")
+    for arr in (cols, valid, mass, stiff):
+        arr[rows] = np.take_along_axis(arr[rows], order, axis=1)
+    counts = valid.sum(axis=1)
+    indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return indptr, cols[valid], mass[valid], stiff[valid]
+
+
 def create_box(comm: Comm, points, n, cell_type=None, dtype=np.float64) -> Mesh:
     return BoxMesh(comm, points[0], points[1], n)
 
@@ -496,6 +700,29 @@ def assemble_p1_box(mesh: "BoxMesh", Mv: np.ndarray):
     return indptr, cols[valid], mass[valid], stiff[valid]
 
 
+def _lv_maps(n_r: int, n_mu: int, n_phi: int, r_short_endo: float, r_short_epi: float, r_long_endo: float, r_long_epi: float,
+             base: float, apex_cut: float):
+    mu0, mu1_endo, mu1_epi = -math.pi + apex_cut, -math.acos(base / r_long_endo), -math.acos(base / r_long_epi)
+
+    def decode(g):
+        g = np.asarray(g)
+        return g // ((n_mu + 1) * n_phi), (g // n_phi) % (n_mu + 1), g % n_phi  # (i_r, i_mu, i_phi)
+
+    def coords_ijk(c, b, a):  # x = phi index, y = mu index, z = transmural index
+        lam = np.asarray(a) / n_r
+        rs = r_short_endo + lam * (r_short_epi - r_short_endo)
+        rl = r_long_endo + lam * (r_long_epi - r_long_endo)
+        mu = mu0 + (np.asarray(b) / n_mu) * ((mu1_endo + lam * (mu1_epi - mu1_endo)) - mu0)
+        phi = 2.0 * math.pi * (np.asarray(c) % n_phi) / n_phi
+        return np.stack([rl * np.cos(mu), rs * np.sin(mu) * np.cos(phi), rs * np.sin(mu) * np.sin(phi)], axis=-1)
+
+    def on_boundary_ids(fg):  # facet (nf, 3) global vertex ids -> exterior?
+        a, b, _ = decode(fg)
+        return (np.all(a == 0, axis=1) | np.all(a == n_r, axis=1) | np.all(b == 0, axis=1) | np.all(b == n_mu, axis=1))
+
+    return decode, coords_ijk, on_boundary_ids
+
+
 def create_lv_ellipsoid(comm: Comm, n_r: int, n_mu: int, n_phi: int, r_short_endo: float = 2.5, r_short_epi: float = 3.5,
                         r_long_endo: float = 9.0, r_long_epi: float = 9.7, base: float = 0.0, apex_cut: float = 0.25) -> Mesh:
     """Synthetic truncated prolate-ellipsoid shell in the spirit of demos/lv_endocardial.py:35-58 (radii from there; the
@@ -503,50 +730,42 @@ def create_lv_ellipsoid(comm: Comm, n_r: int, n_mu: int, n_phi: int, r_short_end
     phi) grid, periodic in phi, Kuhn-split into tetrahedra.  x = r_long cos(mu) is the long axis, the apex (mu = -pi)
     is cut off at mu = -pi + apex_cut to avoid the degenerate pole.  Partition: phi sectors (periodic: the first and
     the last rank are neighbours).  Vertex id = (i_r (n_mu+1) + i_mu) n_phi + i_phi; mesh.info carries the index maps
-    needed for markers (transmural layer of a vertex, exterior surfaces)."""
+    needed for markers (transmural layer of a vertex, exterior surfaces).  Built by index arithmetic (ShellMesh)."""
+    decode, coords_ijk, on_boundary_ids = _lv_maps(n_r, n_mu, n_phi, r_short_endo, r_short_epi, r_long_endo, r_long_epi, base, apex_cut)
+    return ShellMesh(comm, (n_phi, n_mu, n_r), coords_ijk,
+                     info={"kind": "lv_ellipsoid", "n": (n_r, n_mu, n_phi), "on_boundary_ids": on_boundary_ids, "decode": decode})
+
+
+def _create_lv_ellipsoid_generic(comm: Comm, n_r: int, n_mu: int, n_phi: int, r_short_endo: float = 2.5, r_short_epi: float = 3.5,
+                                 r_long_endo: float = 9.0, r_long_epi: float = 9.7, base: float = 0.0, apex_cut: float = 0.25) -> Mesh:
+    """The same mesh through the generic builder (cell array + np.unique): kept as the cross-check of ShellMesh."""
+    decode, coords_ijk, on_boundary_ids = _lv_maps(n_r, n_mu, n_phi, r_short_endo, r_short_epi, r_long_endo, r_long_epi, base, apex_cut)
     starts = _partition_1d(n_phi, comm.size)
     lo, hi = int(starts[comm.rank]), int(starts[comm.rank + 1])
-    cols = np.arange(lo - 1, hi) % n_phi if comm.size > 1 else np.arange(n_phi)  # hexahedra columns touching owned vertices
-    cols = np.unique(cols)
+    cols = np.arange(lo - 1, hi) if comm.size > 1 else np.arange(n_phi)  # unwrapped cube columns, as ShellMesh orders them
     ir, im, ip = np.meshgrid(np.arange(n_r), np.arange(n_mu), cols, indexing="ij")
     ir, im, ip = ir.ravel(), im.ravel(), ip.ravel()
 
-    def vid(a, b, c):
+    def vid(c, b, a):
         return (a * (n_mu + 1) + b) * n_phi + (c % n_phi)
 
-    corner = {(da, db, dc): vid(ir + da, im + db, ip + dc) for da in (0, 1) for db in (0, 1) for dc in (0, 1)}
     tets = []
-    for perm in _KUHN_PERMS:
+    for perm in _KUHN_PERMS:  # steps along (phi, mu, transmural) in the order the permutation says
         off = [0, 0, 0]
-        verts = [corner[tuple(off)]]
+        verts = [vid(ip, im, ir)]
         for ax in perm:
             off[ax] += 1
-            verts.append(corner[tuple(off)])
+            verts.append(vid(ip + off[0], im + off[1], ir + off[2]))
         tets.append(np.stack(verts, axis=1))
     cells = np.concatenate(tets, axis=0).astype(np.int64)
-    mu0, mu1_endo, mu1_epi = -math.pi + apex_cut, -math.acos(base / r_long_endo), -math.acos(base / r_long_epi)
-
-    def decode(g):
-        g = np.asarray(g)
-        return g // ((n_mu + 1) * n_phi), (g // n_phi) % (n_mu + 1), g % n_phi
 
     def coords(g):
         a, b, c = decode(g)
-        lam = a / n_r
-        rs = r_short_endo + lam * (r_short_epi - r_short_endo)
-        rl = r_long_endo + lam * (r_long_epi - r_long_endo)
-        mu = mu0 + (b / n_mu) * ((mu1_endo + lam * (mu1_epi - mu1_endo)) - mu0)
-        phi = 2.0 * math.pi * c / n_phi
-        return np.stack([rl * np.cos(mu), rs * np.sin(mu) * np.cos(phi), rs * np.sin(mu) * np.sin(phi)], axis=1)
+        return coords_ijk(c, b, a)
 
-    def on_boundary_ids(fg):  # facet (nf, 3) global vertex ids -> exterior?
-        a, b, _ = decode(fg)
-        return (np.all(a == 0, axis=1) | np.all(a == n_r, axis=1) | np.all(b == 0, axis=1) | np.all(b == n_mu, axis=1))
-
-    n_global = (n_r + 1) * (n_mu + 1) * n_phi
-    mesh = _build_local(comm, cells, coords, lambda g: np.searchsorted(starts, np.asarray(g) % n_phi, side="right") - 1, n_global, 3,
+    return _build_local(comm, cells, coords, lambda g: np.searchsorted(starts, np.asarray(g) % n_phi, side="right") - 1,
+                        (n_r + 1) * (n_mu + 1) * n_phi, 3,
                         {"kind": "lv_ellipsoid", "n": (n_r, n_mu, n_phi), "on_boundary_ids": on_boundary_ids, "decode": decode})
-    return mesh
 
 
 # ---------------------------------------------------------------------------- entities and tags
@@ -566,7 +785,7 @@ def locate_entities(mesh: Mesh, dim: int, marker: Callable[[np.ndarray], np.ndar
     """Entities whose vertices ALL satisfy ``marker(x)`` (x has shape (3, npoints)), dolfinx semantics."""
     ok = np.asarray(marker(mesh.geometry.x.T), dtype=bool)
     if dim == mesh.topology.dim:
-        if isinstance(mesh, BoxMesh):
+        if isinstance(mesh, (BoxMesh, ShellMesh)):
             return mesh.locate_cells(ok)
         return np.nonzero(ok[mesh.cells].all(axis=1))[0].astype(np.int32)
     if dim == 0:
@@ -876,6 +1095,8 @@ def assemble_p1_local(mesh: Mesh, M) -> tuple[np.ndarray, np.ndarray, np.ndarray
     Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
     if isinstance(mesh, BoxMesh) and Mv.ndim in (0, 2) and not os.environ.get("MONO_GENERIC_ASSEMBLY"):
         return assemble_p1_box(mesh, Mv)
+    if isinstance(mesh, ShellMesh) and not os.environ.get("MONO_GENERIC_ASSEMBLY"):
+        return assemble_p1_structured(mesh, Mv)
     cells = mesh.cells
     n_owned = mesh.index_map.size_local
     n_local = mesh.num_local_vertices

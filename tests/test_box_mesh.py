@@ -73,3 +73,33 @@ def test_lv_ellipsoid_mesh_and_partition():
                 assert np.array_equal(sent, held)
             area += fem.load_vector(g.mesh, fem.Measure("ds", domain=g.mesh, subdomain_data=g.ffun), 1).sum()
         assert np.isclose(area, endo_area)
+
+
+@pytest.mark.parametrize("n", [(3, 6, 12), (2, 5, 9)])
+@pytest.mark.parametrize("size", [1, 2, 3, 4])
+def test_shell_mesh_matches_generic_builder(n, size):
+    """ShellMesh (periodic index arithmetic + stencil assembly with varying element matrices) == the generic builder
+    (cell array, np.unique, scipy accumulation) for the LV shell: numbering, halo lists, cells, matrices with a
+    cell-wise tensor, facet loads."""
+    rng = np.random.default_rng(0)
+    for rank in range(size):
+        comm = fem.Comm(rank, size)
+        a, b = fem.create_lv_ellipsoid(comm, *n), fem._create_lv_ellipsoid_generic(comm, *n)
+        ia, ib = a.index_map, b.index_map
+        assert ia.size_local == ib.size_local and ia.size_global == ib.size_global
+        for name in ("ghosts", "owners", "local_to_global", "nbr_ranks", "send_ptr", "send_idx", "recv_ptr"):
+            assert np.array_equal(getattr(ia, name), getattr(ib, name)), (name, rank, size)
+        assert np.allclose(a.geometry.x, b.geometry.x, atol=1e-15)
+        assert np.array_equal(a.cells, b.cells)
+        A = rng.standard_normal((a.num_cells, 3, 3))
+        Mcell = A @ A.transpose(0, 2, 1) + 0.1 * np.eye(3)  # SPD per cell
+        for Mv in (Mcell, np.diag([3.0, 1.0, 0.5]), 0.7):
+            pa = fem.assemble_p1_local(a, Mv)
+            pb = fem.assemble_p1_local(b, Mv)
+            assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+            assert np.abs(pa[2] - pb[2]).max() <= 1e-14 * np.abs(pb[2]).max()
+            assert np.abs(pa[3] - pb[3]).max() <= 1e-12 * np.abs(pb[3]).max()
+        fa, fb = a.boundary_facets(), b.boundary_facets()
+        assert np.array_equal(fa, fb)
+        marker = lambda x: x[0] > 2.0  # noqa: E731
+        assert np.array_equal(fem.locate_entities(a, 3, marker), fem.locate_entities(b, 3, marker))

@@ -82,6 +82,8 @@ SIGNATURES = {
     "mono_bench_grid_sync": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mono_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "mono_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
+    "mono_fem_assemble_p1": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_int64_p, c_double_p, C.c_int, C.c_int, c_double_p,
+                                       c_int64_p, c_int32_p, c_double_p, c_double_p]),
 }
 
 _lib = None
@@ -180,6 +182,37 @@ def _f64(a, shape=None) -> np.ndarray:
     if shape is not None and a.shape != shape:
         raise ValueError(f"expected shape {shape}, got {a.shape}")
     return a
+
+
+def fem_assemble_p1(tdim: int, n_owned: int, cells: np.ndarray, x: np.ndarray, M) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """mono_fem_assemble_p1 (host threads, no GPU): CSR (indptr, indices, mass, stiff) of the owned rows.
+    cells (ncell, tdim+1) local vertex ids, x (n_local, >= tdim), M scalar | (tdim, tdim) | (ncell, tdim, tdim)."""
+    lib = load_library()
+    cells = np.ascontiguousarray(cells, dtype=np.int64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    Mv = np.asarray(M, dtype=np.float64)  # (ascontiguousarray would turn a scalar into shape (1,))
+    if cells.ndim != 2 or cells.shape[1] != tdim + 1 or x.ndim != 2 or x.shape[1] < tdim:
+        raise ValueError("cells must be (ncell, tdim+1) and x (n_local, >= tdim)")
+    if Mv.size == 1 and Mv.ndim < 2:
+        kind = 0
+    elif Mv.shape == (tdim, tdim):
+        kind = 1
+    elif Mv.shape == (cells.shape[0], tdim, tdim):
+        kind = 2
+    else:
+        raise ValueError(f"conductivity of shape {Mv.shape} fits neither a scalar, a tensor nor one tensor per cell")
+    Mv = np.ascontiguousarray(Mv).reshape(-1)
+    indptr = np.zeros(n_owned + 1, dtype=np.int64)
+    head = (int(tdim), int(x.shape[0]), int(n_owned), int(cells.shape[0]), _i64p(cells), _dp(x), int(x.shape[1]), kind, _dp(Mv), _i64p(indptr))
+    rc = lib.mono_fem_assemble_p1(*head, None, None, None)
+    if rc == 0:
+        nnz = int(indptr[-1])
+        indices = np.empty(nnz, dtype=np.int32)
+        mass, stiff = np.empty(nnz), np.empty(nnz)
+        rc = lib.mono_fem_assemble_p1(*head, _i32p(indices), _dp(mass), _dp(stiff))
+    if rc != 0:
+        raise MonoError(f"mono_fem_assemble_p1 failed ({rc}): {lib.mono_last_error(None).decode()}")
+    return indptr, indices, mass, stiff
 
 
 class Context:

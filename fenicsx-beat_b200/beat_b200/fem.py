@@ -1089,14 +1089,25 @@ def _simplex_measure_and_gradients(x: np.ndarray):
 def assemble_p1_local(mesh: Mesh, M) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
     """CSR (indptr int64, indices int32, mass, stiff) of the OWNED rows over local columns.
 
-    M: scalar, (d,d) tensor, or per-cell (ncell,d,d) tensor.  Entries are accumulated by sorting the
-    (row, col) keys - no dense or scipy intermediate - and both matrices share the sparsity."""
+    M: scalar, (d,d) tensor, or per-cell (ncell,d,d) tensor.  Both matrices share one sparsity with sorted columns.
+    Structured meshes take the stencil routes (index arithmetic, no cell array)."""
     d = mesh.topology.dim
     Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
     if isinstance(mesh, BoxMesh) and Mv.ndim in (0, 2) and not os.environ.get("MONO_GENERIC_ASSEMBLY"):
         return assemble_p1_box(mesh, Mv)
-    if isinstance(mesh, ShellMesh) and not os.environ.get("MONO_GENERIC_ASSEMBLY"):
-        return assemble_p1_structured(mesh, Mv)
+    if isinstance(mesh, ShellMesh) and os.environ.get("MONO_STENCIL_ASSEMBLY"):
+        return assemble_p1_structured(mesh, Mv)  # NumPy stencil route, ~7x slower than the library on 8 cores
+    # everything else: the library's multi-threaded host assembler (rows gathered from their incident cells)
+    from ._lib import fem_assemble_p1
+
+    return fem_assemble_p1(d, mesh.index_map.size_local, mesh.cells, mesh.geometry.x, Mv)
+
+
+def _assemble_p1_numpy(mesh: Mesh, M):
+    """NumPy/SciPy restatement of the library's assembler (element matrices of all cells at once, duplicates summed by
+    scipy's coo -> csr).  Kept as the cross-check of mono_fem_assemble_p1 in the tests."""
+    d = mesh.topology.dim
+    Mv = np.asarray(M.value if isinstance(M, Constant) else M, dtype=np.float64)
     cells = mesh.cells
     n_owned = mesh.index_map.size_local
     n_local = mesh.num_local_vertices
@@ -1115,8 +1126,6 @@ def assemble_p1_local(mesh: Mesh, M) -> tuple[np.ndarray, np.ndarray, np.ndarray
     cols = np.broadcast_to(cells[:, None, :], Ke.shape).ravel()
     keep = rows < n_owned
     rows, cols = rows[keep], cols[keep]
-    # duplicates are summed by scipy's C routines (coo -> csr); both matrices get the same pattern (structural zeros of
-    # K stay in), columns sorted within a row
     import scipy.sparse as sp
 
     mass_m = sp.coo_matrix((Me.ravel()[keep], (rows, cols)), shape=(n_owned, n_local)).tocsr()

@@ -18,7 +18,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "beat_b200", "libmono_b200.so")
-SOURCES = ["mono_ctx.cu", "ode_kernels.cu", "pde_kernels.cu", "halo.cu"]
+SOURCES = ["mono_ctx.cu", "ode_kernels.cu", "pde_kernels.cu", "halo.cu", "fem_assemble.cu"]  # the last one is host-only C++
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             list(ex.map(compile_one, jobs))
     if jobs or force or not os.path.exists(OUT):
-        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-ldl"]  # NCCL is dlopen'ed at mono_comm_init (halo.cu)
+        cmd = [nvcc, "-shared", "-o", OUT, *objs, "-ldl", "-lpthread"]  # NCCL is dlopen'ed at mono_comm_init (halo.cu)
         if verbose:
             print("[build]", " ".join(cmd), flush=True)
         subprocess.run(cmd, check=True)

@@ -11,7 +11,8 @@
  *   - plain C, no torch / CUDA types; all arrays are HOST pointers unless the name says `_dev`.
  *   - all arithmetic is fp64; indices are int32 (CSR) / int64 (sizes).
  *   - every function returns 0 on success and a negative MONO_E_* code on failure; the message is
- *     available from mono_last_error(ctx) (ctx == NULL: error of the last failed mono_ctx_create).
+ *     available from mono_last_error(ctx) (ctx == NULL: error of the last failed context-free call,
+ *     i.e. mono_ctx_create or mono_fem_assemble_p1, of this thread).
  *     CUDA / NCCL failures never abort the process.
  *   - one context per process-rank and GPU; a context is NOT thread-safe; work is queued on the
  *     context's own CUDA stream and is asynchronous unless documented otherwise (`get`/`info` calls
@@ -194,6 +195,20 @@ int mono_probe_values(mono_ctx *ctx, double *values); /* current value of every 
  * (niederer_benchmark.py:284-287); -1 while not activated.                                         */
 int mono_probe_activation(mono_ctx *ctx, double threshold);
 int mono_probe_activation_times(mono_ctx *ctx, double *times);
+
+/* ---- host-side set-up helper (no GPU involved) -------------------------------------------------- */
+/* P1 simplex assembly of the OWNED rows (0..n_owned-1) of the mass matrix  v*w*dx  and the stiffness matrix
+ * inner(M grad v, grad w)*dx  (the two forms of monodomain_model.py:96-118 without their constant factors) over the
+ * local columns, both on one sparsity with sorted columns: what dolfinx.fem.assemble_matrix provides in the reference
+ * and mono_pde_set_matrices takes here.  For hosts that bring a mesh as plain arrays instead of a dolfinx mesh.
+ *   tdim 1..3; cells: n_cells x (tdim+1) local vertex ids, row-major; x: n_local rows of x_ld >= tdim doubles;
+ *   m_kind 0: scalar M[0], 1: constant tensor M[tdim*tdim], 2: one tensor per cell M[n_cells*tdim*tdim] (row-major).
+ * Two calls: with indices == NULL only indptr[n_owned+1] is written (indptr[n_owned] = nnz); the second call, with
+ * that indptr, fills indices/mass/stiff.  Multi-threaded (MONO_HOST_THREADS, default min(cores, 16)), deterministic.
+ * Errors are reported through mono_last_error(NULL). */
+int mono_fem_assemble_p1(int tdim, int64_t n_local, int64_t n_owned, int64_t n_cells, const int64_t *cells,
+                         const double *x, int x_ld, int m_kind, const double *M, int64_t *indptr, int32_t *indices,
+                         double *mass, double *stiff);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------- */
 /* CUDA-event stopwatch on the context's stream: start/stop record events, elapsed synchronises. */

@@ -94,11 +94,11 @@ def test_shell_mesh_matches_generic_builder(n, size):
         A = rng.standard_normal((a.num_cells, 3, 3))
         Mcell = A @ A.transpose(0, 2, 1) + 0.1 * np.eye(3)  # SPD per cell
         for Mv in (Mcell, np.diag([3.0, 1.0, 0.5]), 0.7):
-            pa = fem.assemble_p1_local(a, Mv)
-            pb = fem.assemble_p1_local(b, Mv)
-            assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
-            assert np.abs(pa[2] - pb[2]).max() <= 1e-14 * np.abs(pb[2]).max()
-            assert np.abs(pa[3] - pb[3]).max() <= 1e-12 * np.abs(pb[3]).max()
+            pb = fem._assemble_p1_numpy(b, Mv)
+            for pa in (fem.assemble_p1_local(a, Mv), fem.assemble_p1_structured(a, np.asarray(Mv))):  # library threads / NumPy stencils
+                assert np.array_equal(pa[0], pb[0]) and np.array_equal(pa[1], pb[1])
+                assert np.abs(pa[2] - pb[2]).max() <= 1e-14 * np.abs(pb[2]).max()
+                assert np.abs(pa[3] - pb[3]).max() <= 1e-12 * np.abs(pb[3]).max()
         fa, fb = a.boundary_facets(), b.boundary_facets()
         assert np.array_equal(fa, fb)
         marker = lambda x: x[0] > 2.0  # noqa: E731

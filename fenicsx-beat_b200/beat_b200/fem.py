@@ -364,8 +364,20 @@ class BoxMesh(Mesh):
 
     @property
     def cells(self) -> np.ndarray:
+        """All local cells, cell id = perm * num_cubes + cube.  The 8 corners of every cube are indexed once and the six
+        Kuhn tets pick their 4 from them (same rows as cells_of(arange), a third of the index arithmetic)."""
         if self._cells is None:
-            self._cells = self.cells_of(np.arange(self.num_cells, dtype=np.int64))
+            ncube = self.num_cubes
+            i, j, k = self._cube_ijk(np.arange(ncube, dtype=np.int64))
+            corner = {(dx_, dy_, dz_): self.local_index(i + dx_, j + dy_, k + dz_) for dx_ in (0, 1) for dy_ in (0, 1) for dz_ in (0, 1)}
+            out = np.empty((6, ncube, 4), dtype=np.int64)
+            for p, perm in enumerate(_KUHN_PERMS):
+                off = [0, 0, 0]
+                out[p, :, 0] = corner[0, 0, 0]
+                for a in range(3):
+                    off[perm[a]] += 1
+                    out[p, :, a + 1] = corner[tuple(off)]
+            self._cells = out.reshape(-1, 4)
         return self._cells
 
     def locate_cells(self, ok: np.ndarray) -> np.ndarray:

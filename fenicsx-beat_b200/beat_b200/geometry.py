@@ -74,17 +74,24 @@ def get_lv_ellipsoid_geometry(comm, n_r: int = 4, n_mu: int = 24, n_phi: int = 3
     layer = np.minimum(3 * a // (n_r + 1), 2) + 1  # vertex layer 1..3
     mesh.info["endo_epi"] = layer.astype(np.float64)
     # fibres at the cell centroids: circumferential / longitudinal frame of the local ellipsoid coordinates
-    X = mesh.geometry.x[mesh.cells].mean(axis=1)
-    lam = a[mesh.cells].mean(axis=1) / n_r
-    e_phi = np.stack([np.zeros(X.shape[0]), -X[:, 2], X[:, 1]], axis=1)
-    e_phi /= np.linalg.norm(e_phi, axis=1, keepdims=True)
+    # (component arrays throughout: row-wise reductions over (ncell, 3) temporaries cost several times more in NumPy)
+    cells, xv = mesh.cells, mesh.geometry.x
+    corners = [np.ascontiguousarray(cells[:, q]) for q in range(4)]
+    X, Y, Z = (0.25 * (xv[corners[0], d] + xv[corners[1], d] + xv[corners[2], d] + xv[corners[3], d]) for d in range(3))
+    lam = (a[corners[0]] + a[corners[1]] + a[corners[2]] + a[corners[3]]) * (0.25 / n_r)
+    inv = 1.0 / np.sqrt(Y * Y + Z * Z)
+    ephi_y, ephi_z = -Z * inv, Y * inv  # e_phi = (0, -z, y) / |.|
     # surface normal of the ellipsoid through the point (gradient of x^2/rl^2 + (y^2+z^2)/rs^2), then e_mu = n x e_phi
     rs = radii.get("r_short_endo", 2.5) + lam * (radii.get("r_short_epi", 3.5) - radii.get("r_short_endo", 2.5))
     rl = radii.get("r_long_endo", 9.0) + lam * (radii.get("r_long_epi", 9.7) - radii.get("r_long_endo", 9.0))
-    nrm = np.stack([X[:, 0] / rl**2, X[:, 1] / rs**2, X[:, 2] / rs**2], axis=1)
-    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
-    e_mu = np.cross(nrm, e_phi)
+    nx_, ny_, nz_ = X / rl**2, Y / rs**2, Z / rs**2
+    inv = 1.0 / np.sqrt(nx_ * nx_ + ny_ * ny_ + nz_ * nz_)
+    nx_, ny_, nz_ = nx_ * inv, ny_ * inv, nz_ * inv
+    emu = (ny_ * ephi_z - nz_ * ephi_y, -nx_ * ephi_z, nx_ * ephi_y)
     alpha = np.deg2rad(fiber_angle_endo + lam * (fiber_angle_epi - fiber_angle_endo))
-    f0 = np.cos(alpha)[:, None] * e_phi + np.sin(alpha)[:, None] * e_mu
-    f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+    ca, sa = np.cos(alpha), np.sin(alpha)
+    fx, fy, fz = sa * emu[0], ca * ephi_y + sa * emu[1], ca * ephi_z + sa * emu[2]
+    inv = 1.0 / np.sqrt(fx * fx + fy * fy + fz * fz)
+    f0 = np.stack([fx * inv, fy * inv, fz * inv], axis=1)
+    nrm = np.stack([nx_, ny_, nz_], axis=1)
     return Geometry(mesh=mesh, ffun=ffun, markers=markers, f0=f0, n0=nrm)

@@ -165,6 +165,7 @@ extern "C" {
 
 int mono_comm_unique_id(void* id_out128) {
   static_assert(sizeof(ncclUniqueId) == 128, "NCCL unique id is 128 bytes");
+  if (!id_out128) return mono_fail(nullptr, MONO_E_INVALID, "id_out128 is NULL");
   if (!nccl_load()) return mono_fail(nullptr, MONO_E_NCCL, g_nccl.error);
   ncclUniqueId id;
   ncclResult_t r = g_nccl.GetUniqueId(&id);
@@ -180,6 +181,7 @@ int mono_comm_init(mono_ctx* c, int nranks, int rank, const void* id128) {
   c->nranks = nranks;
   c->rank = rank;
   if (nranks == 1) return MONO_OK;
+  MONO_CHECK(c, id128 != nullptr, "id128 is NULL");
   if (!nccl_load()) return mono_fail(c, MONO_E_NCCL, g_nccl.error);
   MONO_CUDA(c, cudaSetDevice(c->device));
   ncclUniqueId id;
@@ -196,6 +198,11 @@ int mono_set_halo(mono_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_
                   const int32_t* recv_ptr) {
   MONO_CHECK(c, c->has_pde, "set matrices before the halo pattern");
   MONO_CHECK(c, n_nbr >= 0, "negative neighbour count");
+  MONO_CHECK(c, send_ptr && recv_ptr && (n_nbr == 0 || nbr_ranks), "halo arrays are NULL");
+  MONO_CHECK(c, send_ptr[0] == 0 && recv_ptr[0] == 0, "send_ptr / recv_ptr must start at 0");
+  for (int k = 0; k < n_nbr; ++k)
+    MONO_CHECK(c, send_ptr[k + 1] >= send_ptr[k] && recv_ptr[k + 1] >= recv_ptr[k], "send_ptr / recv_ptr must be non-decreasing");
+  MONO_CHECK(c, send_ptr[n_nbr] == 0 || send_idx, "send_idx is NULL");
   c->n_nbr = n_nbr;
   c->nbr_ranks.assign(nbr_ranks, nbr_ranks + n_nbr);
   c->send_ptr.assign(send_ptr, send_ptr + n_nbr + 1);

@@ -209,6 +209,7 @@ int mono_sync(mono_ctx* c) {
 }
 
 int mono_device_info(mono_ctx* c, int* n_sm, int* cc_major, int* cc_minor, int64_t* mem_bytes) {
+  MONO_NEED_CTX(c);
   cudaDeviceProp prop;
   MONO_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
   if (n_sm) *n_sm = prop.multiProcessorCount;
@@ -472,6 +473,7 @@ int mono_stim_add(mono_ctx* c, int64_t nnz, const int32_t* idx, const double* va
                   double amplitude) {
   MONO_CHECK(c, c->has_pde, "set matrices before adding stimuli");
   MONO_CHECK(c, nnz >= 0, "negative nnz");
+  MONO_CHECK(c, nnz == 0 || (idx && val), "stimulus arrays are NULL");
   for (int64_t k = 0; k < nnz; ++k) MONO_CHECK(c, idx[k] >= 0 && idx[k] < c->n_owned, "stimulus index is not an owned dof");
   StimDev s{};
   s.nnz = nnz;
@@ -497,9 +499,7 @@ int mono_stim_add(mono_ctx* c, int64_t nnz, const int32_t* idx, const double* va
 
 int mono_stim_set_amplitude(mono_ctx* c, int id, double amplitude) {
   MONO_CHECK(c, id >= 0 && id < (int)c->stims_host.size(), "bad stimulus id");
-  if (c->stims_host[id].amp != amplitude) {
-    c->stims_host[id].amp = amplitude;
-    }
+  c->stims_host[id].amp = amplitude;  // pde_launch_step notices the change and rebuilds the dense source vector
   return MONO_OK;
 }
 
@@ -637,7 +637,7 @@ int mono_split_solve(mono_ctx* c, double t0, double dt, int64_t nsteps, double t
 // ---------------------------------------------------------------------------------------- observers
 int mono_probe_add(mono_ctx* c, int n_nodes, const int32_t* nodes, const double* weights) {
   MONO_CHECK(c, c->has_pde, "set matrices before adding probes");
-  MONO_CHECK(c, n_nodes >= 1 && n_nodes <= 4, "a probe has 1..4 nodes");
+  MONO_CHECK(c, n_nodes >= 1 && n_nodes <= 4 && nodes && weights, "a probe has 1..4 nodes");
   ProbeDev p{};
   p.n = n_nodes;
   for (int k = 0; k < n_nodes; ++k) {
@@ -651,6 +651,7 @@ int mono_probe_add(mono_ctx* c, int n_nodes, const int32_t* nodes, const double*
 }
 
 int mono_probe_values(mono_ctx* c, double* values) {
+  MONO_NEED_CTX(c);
   const int n = (int)c->probes_host.size();
   if (n == 0) return MONO_OK;
   int rc = probes_launch(c, -1.0e300);  // evaluates; cannot activate (t0 only stored when crossing)
@@ -659,12 +660,14 @@ int mono_probe_values(mono_ctx* c, double* values) {
 }
 
 int mono_probe_activation(mono_ctx* c, double threshold) {
+  MONO_NEED_CTX(c);
   c->act_enabled = true;
   c->act_threshold = threshold;
   return MONO_OK;
 }
 
 int mono_probe_activation_times(mono_ctx* c, double* times) {
+  MONO_NEED_CTX(c);
   const int n = (int)c->probes_host.size();
   if (n == 0) return MONO_OK;
   if (c->probes_dirty) {
@@ -714,6 +717,7 @@ int mono_event_elapsed_ms(mono_ctx* c, int idx0, int idx1, float* ms) {
 }
 
 int mono_l2_flush(mono_ctx* c) {
+  MONO_NEED_CTX(c);
   if (!c->flush_buf) {
     c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
     MONO_CUDA(c, cudaMalloc(&c->flush_buf, c->flush_bytes));
@@ -723,11 +727,13 @@ int mono_l2_flush(mono_ctx* c) {
 }
 
 int mono_stage_timing(mono_ctx* c, int enable) {
+  MONO_NEED_CTX(c);
   c->stage_timing = enable != 0;
   return MONO_OK;
 }
 
 int mono_stage_times_ms(mono_ctx* c, double* ms2, int64_t* steps, int reset) {
+  MONO_NEED_CTX(c);
   int rc = drain_stage_events(c);
   if (rc) return rc;
   if (ms2) {
@@ -743,6 +749,7 @@ int mono_stage_times_ms(mono_ctx* c, double* ms2, int64_t* steps, int reset) {
 }
 
 int mono_bench_dfma(mono_ctx* c, double* tflops) {
+  MONO_NEED_CTX(c);
   double* out = nullptr;
   MONO_CUDA(c, cudaMalloc(&out, sizeof(double)));
   const int blocks = c->n_sm * 8, threads = 256, iters = 4096;
@@ -768,6 +775,7 @@ int mono_bench_dfma(mono_ctx* c, double* tflops) {
 }
 
 int mono_debug_timeline(mono_ctx* c, int enable, uint64_t* stamps64) {
+  MONO_NEED_CTX(c);
   if (enable && !c->timeline_dev) {
     MONO_CUDA(c, cudaMalloc(&c->timeline_dev, sizeof(unsigned long long) * 64));
     MONO_CUDA(c, cudaMemsetAsync(c->timeline_dev, 0, sizeof(unsigned long long) * 64, c->stream));
@@ -790,6 +798,7 @@ int mono_bench_grid_sync(mono_ctx* c, int n, float* us_per_sync) {
 }
 
 int mono_launch_count(mono_ctx* c, int64_t* launches) {
+  MONO_NEED_CTX(c);
   if (launches) *launches = c->launches;
   return MONO_OK;
 }

@@ -153,15 +153,22 @@ struct mono_ctx {
 
 // ---- helpers shared by the translation units ---------------------------------------------------
 int mono_fail(mono_ctx* c, int code, const std::string& msg);
+// Both macros refuse a NULL context first, so every entry point that starts with one of them is safe to call with NULL.
 #define MONO_CUDA(c, call)                                                                          \
   do {                                                                                              \
+    if (!(c)) return mono_fail(nullptr, MONO_E_INVALID, "ctx is NULL");                             \
     cudaError_t e__ = (call);                                                                       \
     if (e__ != cudaSuccess)                                                                         \
       return mono_fail((c), MONO_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));     \
   } while (0)
-#define MONO_CHECK(c, cond, msg)                          \
-  do {                                                    \
-    if (!(cond)) return mono_fail((c), MONO_E_INVALID, (msg)); \
+#define MONO_NEED_CTX(c)                                                \
+  do {                                                                  \
+    if (!(c)) return mono_fail(nullptr, MONO_E_INVALID, "ctx is NULL"); \
+  } while (0)
+#define MONO_CHECK(c, cond, msg)                                        \
+  do {                                                                  \
+    if (!(c)) return mono_fail(nullptr, MONO_E_INVALID, "ctx is NULL"); \
+    if (!(cond)) return mono_fail((c), MONO_E_INVALID, (msg));          \
   } while (0)
 
 // ode_kernels.cu

@@ -1221,6 +1221,14 @@ __global__ void probes_kernel(int n_probes, const ProbeDev* __restrict__ probes,
 int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, const double* mass, const double* stiff) {
   const int64_t n = c->n_owned;
   const int64_t ns = (n + kSlice - 1) / kSlice;
+  MONO_CHECK(c, indptr && (n == 0 || (indices && mass && stiff)), "CSR arrays are NULL");
+  MONO_CHECK(c, indptr[0] == 0, "indptr[0] must be 0");
+  for (int64_t r = 0; r < n; ++r) {
+    MONO_CHECK(c, indptr[r + 1] >= indptr[r], "indptr is not non-decreasing");
+    bool diag = false;
+    for (int64_t k = indptr[r]; k < indptr[r + 1] && !diag; ++k) diag = indices[k] == r;
+    MONO_CHECK(c, diag, "every owned row needs its diagonal entry (Jacobi scaling, mass matrix)");
+  }
   std::vector<int64_t> sp(ns + 1, 0);
   for (int64_t s = 0; s < ns; ++s) {
     int64_t w = 0;

@@ -40,3 +40,26 @@ def test_no_cpu_fallback_without_device():
 
     with pytest.raises(RuntimeError, match="(?i)cuda|device"):
         _lib.Context(0)
+
+
+def test_binding_table_covers_the_header():
+    from beat_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == declared_functions()
+
+
+def test_null_context_is_refused_not_dereferenced():
+    """Every entry point that takes a context answers MONO_E_INVALID to NULL (no GPU needed to check that)."""
+    from beat_b200 import _lib
+
+    lib = _lib.load_library()
+    checked = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if not args or args[0] is not ctypes.c_void_p or res is not ctypes.c_int or name in ("mono_ctx_destroy", "mono_host_free"):
+            continue
+        zeros = [None if a is ctypes.c_void_p or hasattr(a, "contents") else 0 for a in args]
+        assert getattr(lib, name)(*zeros) == -1, name
+        assert b"NULL" in lib.mono_last_error(None), name
+        checked += 1
+    assert checked >= 50
+    assert lib.mono_ctx_destroy(None) == 0

@@ -82,6 +82,8 @@ SIGNATURES = {
     "mono_bench_grid_sync": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mono_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "mono_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
+    "mono_csr_row_patterns": (C.c_int, [C.c_int64, c_int64_p, c_int32_p, c_double_p, c_double_p, C.c_int, C.POINTER(C.c_uint8),
+                                        c_int32_p, c_int64_p, c_int64_p]),
     "mono_fem_assemble_p1": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_int64_p, c_double_p, C.c_int, C.c_int, c_double_p,
                                        c_int64_p, c_int32_p, c_double_p, c_double_p]),
 }
@@ -213,6 +215,23 @@ def fem_assemble_p1(tdim: int, n_owned: int, cells: np.ndarray, x: np.ndarray, M
     if rc != 0:
         raise MonoError(f"mono_fem_assemble_p1 failed ({rc}): {lib.mono_last_error(None).decode()}")
     return indptr, indices, mass, stiff
+
+
+def csr_row_patterns(indptr, indices, mass, stiff, max_patterns: int = 64):
+    """mono_csr_row_patterns: (pattern_of_row uint8 [255 = not in the dictionary], representative_row, rows_per_pattern)."""
+    lib = load_library()
+    ip = np.ascontiguousarray(indptr, dtype=np.int64)
+    ix = np.ascontiguousarray(indices, dtype=np.int32)
+    m, k = _f64(mass, ix.shape), _f64(stiff, ix.shape)
+    n = ip.size - 1
+    pat = np.empty(n, dtype=np.uint8)
+    npat = np.zeros(1, dtype=np.int32)
+    rep, cnt = np.zeros(max_patterns, dtype=np.int64), np.zeros(max_patterns, dtype=np.int64)
+    rc = lib.mono_csr_row_patterns(n, _i64p(ip), _i32p(ix), _dp(m), _dp(k), int(max_patterns), pat.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                   _i32p(npat), _i64p(rep), _i64p(cnt))
+    if rc != 0:
+        raise MonoError(f"mono_csr_row_patterns failed ({rc}): {lib.mono_last_error(None).decode()}")
+    return pat, rep[: npat[0]], cnt[: npat[0]]
 
 
 class Context:

@@ -18,7 +18,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "beat_b200", "libmono_b200.so")
-SOURCES = ["mono_ctx.cu", "ode_kernels.cu", "pde_kernels.cu", "halo.cu", "fem_assemble.cu"]  # the last one is host-only C++
+SOURCES = ["mono_ctx.cu", "ode_kernels.cu", "pde_kernels.cu", "halo.cu", "fem_assemble.cu", "csr_patterns.cu"]  # the last two are host-only C++
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -12,7 +12,7 @@
  *   - all arithmetic is fp64; indices are int32 (CSR) / int64 (sizes).
  *   - every function returns 0 on success and a negative MONO_E_* code on failure; the message is
  *     available from mono_last_error(ctx) (ctx == NULL: error of the last failed context-free call,
- *     i.e. mono_ctx_create or mono_fem_assemble_p1, of this thread).
+ *     i.e. mono_ctx_create, mono_fem_assemble_p1 or mono_csr_row_patterns, of this thread).
  *     CUDA / NCCL failures never abort the process.
  *   - one context per process-rank and GPU; a context is NOT thread-safe; work is queued on the
  *     context's own CUDA stream and is asynchronous unless documented otherwise (`get`/`info` calls
@@ -209,6 +209,16 @@ int mono_probe_activation_times(mono_ctx *ctx, double *times);
 int mono_fem_assemble_p1(int tdim, int64_t n_local, int64_t n_owned, int64_t n_cells, const int64_t *cells,
                          const double *x, int x_ld, int m_kind, const double *M, int64_t *indptr, int32_t *indices,
                          double *mass, double *stiff);
+
+/* Stencil dictionary of a (mass, stiffness) CSR pair (host threads, no GPU): owned rows are classified by
+ * (column offsets relative to the row, mass values, stiffness values), compared bit for bit.  The max_patterns (1..255)
+ * most frequent stencils are numbered 0.. by frequency (ties: first row); pattern_of_row[r] is that number or 255 for a
+ * row outside the dictionary; representative_row / rows_per_pattern (max_patterns entries each) describe the kept ones.
+ * A structured box (the Niederer slab) has 27 stencils; a mapped or unstructured mesh has as many as rows.  Used to decide
+ * whether the matrix stream of the CG iteration is compressible. */
+int mono_csr_row_patterns(int64_t n_owned, const int64_t *indptr, const int32_t *indices, const double *mass,
+                          const double *stiff, int max_patterns, uint8_t *pattern_of_row, int32_t *n_patterns,
+                          int64_t *representative_row, int64_t *rows_per_pattern);
 
 /* ---- measurement helpers (bench.py) -------------------------------------------------------------- */
 /* CUDA-event stopwatch on the context's stream: start/stop record events, elapsed synchronises. */

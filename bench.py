@@ -194,6 +194,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     comm = fem.Comm(rank, world)
     K, W = args.steps, args.warmup
+    if args.matrix_dict:
+        os.environ["MONO_PDE_DICT"] = "1"  # read by mono_pde_set_matrices
     t_setup = time.perf_counter()
     is_lv = args.workload in LV_WORKLOADS
     if is_lv:
@@ -393,6 +395,10 @@ def run_b200(args):
         "roofline_stages": {"pde": roof_pde, "ode": roof_ode},
         "clocks": clk, "setup_s": setup_s, "v_max_mV": v_max,
     }
+    if args.matrix_dict:
+        line["config"]["matrix_dictionary"] = ctx.pde_dictionary_info()
+        # dictionary rows read 1 byte of pattern id instead of 12 z bytes of SELL entries: the roofline above still uses the
+        # SELL byte count, so `achieved` can exceed what DRAM actually moved - compare ms_per_step, not frac
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline and not is_lv:
             r = cpu_run(dx, dt, steps=2000, warmup=2, budget_s=20.0)
@@ -420,6 +426,9 @@ def main():
                     help="preconditioner (auto: the reference's hypre request mapped to the fastest native one for the mesh size)")
     ap.add_argument("--x0", default="zero", choices=["zero", "previous"],
                     help="initial guess of the diffusion solve: zero = PETSc default (as the reference runs), previous = v_")
+    ap.add_argument("--matrix-dict", action="store_true",
+                    help="EXPERIMENTAL: stencil dictionary for the matrix stream of the streaming KSPCG kernel (MONO_PDE_DICT=1); "
+                         "bit-identical results, not yet measured")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the x0=v_ extra measurement")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

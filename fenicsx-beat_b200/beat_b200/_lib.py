@@ -82,6 +82,7 @@ SIGNATURES = {
     "mono_bench_grid_sync": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
     "mono_debug_timeline": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]),
     "mono_launch_count": (C.c_int, [C.c_void_p, c_int64_p]),
+    "mono_pde_dictionary_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), c_double_p, C.POINTER(C.c_int)]),
     "mono_csr_row_patterns": (C.c_int, [C.c_int64, c_int64_p, c_int32_p, c_double_p, c_double_p, C.c_int, C.POINTER(C.c_uint8),
                                         c_int32_p, c_int64_p, c_int64_p]),
     "mono_fem_assemble_p1": (C.c_int, [C.c_int, C.c_int64, C.c_int64, C.c_int64, c_int64_p, c_double_p, C.c_int, C.c_int, c_double_p,
@@ -376,6 +377,11 @@ class Context:
 
     def pde_config(self, C_m, theta, rtol, atol, max_it, pc_type, norm_type, x0_mode):
         self._ck(self.lib.mono_pde_config(self.h, C_m, theta, rtol, atol, max_it, pc_type, norm_type, x0_mode))
+
+    def pde_dictionary_info(self) -> dict:
+        n, cover, active = C.c_int(0), C.c_double(0.0), C.c_int(0)
+        self._ck(self.lib.mono_pde_dictionary_info(self.h, C.byref(n), C.byref(cover), C.byref(active)))
+        return {"patterns": n.value, "rows_covered": cover.value, "active": bool(active.value)}
 
     def pde_set_chebyshev(self, steps: int, kappa: float):
         self._ck(self.lib.mono_pde_set_chebyshev(self.h, int(steps), float(kappa)))

@@ -171,7 +171,8 @@ int mono_ctx_destroy(mono_ctx* c) {
                   (void*)c->recs, (void*)c->timeline_dev,
                   (void*)c->ksp_dev, (void*)c->probes_dev,
                   (void*)c->probe_vals_dev, (void*)c->probe_act_dev, (void*)c->flush_buf, (void*)c->send_idx_dev,
-                  (void*)c->send_buf, (void*)c->red_buf})
+                  (void*)c->send_buf, (void*)c->red_buf, (void*)c->pat_dev, (void*)c->dict_off_dev, (void*)c->dict_w_dev,
+                  (void*)c->dict_src_dev, (void*)c->dict_A_dev, (void*)c->dict_B_dev})
     if (p) cudaFree(p);
   for (void* p : c->stim_allocs) cudaFree(p);
   if (c->ksp_host) cudaFreeHost(c->ksp_host);
@@ -576,6 +577,14 @@ int mono_ksp_total_iterations(mono_ctx* c, int64_t* total, int64_t* solves) {
   MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   if (total) *total = c->ksp_host->total_iterations;
   if (solves) *solves = c->ksp_host->solves;
+  return MONO_OK;
+}
+
+int mono_pde_dictionary_info(mono_ctx* c, int* n_patterns, double* rows_covered, int* active) {
+  MONO_CHECK(c, c->has_pde, "no PDE matrices");
+  if (n_patterns) *n_patterns = c->n_pat;
+  if (rows_covered) *rows_covered = c->dict_cover;
+  if (active) *active = c->dict_active ? 1 : 0;
   return MONO_OK;
 }
 

@@ -122,6 +122,16 @@ struct mono_ctx {
   bool resident = false;            // the CG vectors of a CTA's rows fit in shared memory
   bool staged = false;              // streaming mode: SELL slices reach the SpMV through TMA-staged shared memory
   size_t resident_smem = 0;
+  // stencil dictionary of the matrices (EXPERIMENTAL, MONO_PDE_DICT=1; pde_build_sell): rows whose (column offsets, values)
+  // repeat take their entries from a small table in shared memory instead of the SELL stream
+  int n_pat = 0;                    // patterns in the dictionary (0: none)
+  double dict_cover = 0.0;          // fraction of the owned rows the dictionary covers
+  bool dict_active = false;         // the current mode runs the dictionary kernel (streaming KSPCG only)
+  uint8_t* pat_dev = nullptr;       // n_owned: pattern of a row, 255 = not in the dictionary
+  int32_t* dict_off_dev = nullptr;  // [n_pat][16] column offsets relative to the row
+  int32_t* dict_w_dev = nullptr;    // [n_pat] entries per pattern
+  int64_t* dict_src_dev = nullptr;  // [n_pat][16] SELL position of the representative row's entries (-1: padding)
+  double *dict_A_dev = nullptr, *dict_B_dev = nullptr;  // [n_pat][16] gathered from A / B after every rebuild
   KspResult* ksp_dev = nullptr;
   KspResult* ksp_host = nullptr;  // pinned
 

@@ -49,6 +49,8 @@ constexpr int kPdeThreads = 512;
 constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
+constexpr int kMaxPat = 64;           // stencil dictionary: patterns (of at most kChunk entries) held in shared memory
+constexpr int kDictSmem = kMaxPat * kChunk * (8 + 8 + 4) + kMaxPat * 4;  // A values, B values, offsets, widths
 typedef unsigned long long u64;
 
 // where one owned boundary value goes on ONE neighbour rank (peer-mapped addresses of its ghost slot)
@@ -94,6 +96,13 @@ struct PdeArgs {
   const SendEnt* send_ents;
   KspResult* res;
   u64* timeline;                    // optional (measurement): globaltimer stamps of CTA 0 at phase boundaries
+  // ---- stencil dictionary (DICT kernels only) ----
+  const uint8_t* pat;               // n_owned: pattern of a row, 255 = take the row from the SELL arrays
+  const double* dict_A;             // [n_pat][kChunk]
+  const double* dict_B;
+  const int32_t* dict_off;          // [n_pat][kChunk] column - row
+  const int32_t* dict_w;            // [n_pat]
+  int n_pat;
 };
 
 __device__ __forceinline__ void stamp(const PdeArgs& a, int& n) {
@@ -504,6 +513,73 @@ __device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool 
   if (a.has_stim && r.row < a.n_owned) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
 }
 
+// ---- stencil dictionary (EXPERIMENTAL) -------------------------------------------------------------------------
+// On a structured mesh almost every row repeats one of a few stencils (27 on a box).  Such rows take their entries
+// from a table in shared memory - column = row + offset - and never touch the SELL stream; the other rows (pattern
+// 255: next to a ghost layer, or a mapped geometry) read their SELL entries as before.  Same entries in the same
+// order as the SELL row, so the products and their sum are bit-identical.
+struct DictView {
+  const double* sA;     // [n_pat][kChunk]
+  const double* sB;
+  const int32_t* sOff;
+  const int32_t* sW;
+};
+
+__device__ __forceinline__ DictView dict_load(const PdeArgs& a, double* dyn_smem) {  // all threads of a worker CTA
+  double* sA = dyn_smem;
+  double* sB = sA + kMaxPat * kChunk;
+  int32_t* sOff = reinterpret_cast<int32_t*>(sB + kMaxPat * kChunk);
+  int32_t* sW = sOff + kMaxPat * kChunk;
+  for (int i = threadIdx.x; i < a.n_pat * kChunk; i += kPdeThreads) {
+    sA[i] = __ldg(a.dict_A + i);
+    sB[i] = __ldg(a.dict_B + i);
+    sOff[i] = __ldg(a.dict_off + i);
+  }
+  for (int i = threadIdx.x; i < a.n_pat; i += kPdeThreads) sW[i] = __ldg(a.dict_w + i);
+  __syncthreads();
+  return DictView{sA, sB, sOff, sW};
+}
+
+// q_row = sum_k A_k * g(col_k), gathered vector tagged (the CG search direction)
+template <bool SYS>
+__device__ __forceinline__ double dict_apply(const PdeArgs& a, const DictView& D, const RowRef& r, const void* vec, u64 want, int* fail) {
+  const int p = (int)__ldg(a.pat + r.row);
+  const bool in_dict = p != 255;
+  const int base = in_dict ? p * kChunk : 0;
+  const int width = in_dict ? D.sW[p] : r.width;
+  double out[1];
+  sell_row<1, true, SYS, false, false>(
+      width, [&](int k) { return in_dict ? (int32_t)r.row + D.sOff[base + k] : __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); },
+      [&](int, int k) { return in_dict ? D.sA[base + k] : __ldg(a.A + r.beg + (int64_t)k * kSlice + r.lane); }, vec, want, fail,
+      a.spin_ns, out);
+  return out[0];
+}
+
+// b = B v_ (+ dt * stimulus) and, for x0 = v_, A x0 in the same pass (the dictionary version of rhs_row)
+__device__ __forceinline__ void dict_rhs_row(const PdeArgs& a, const DictView& D, const RowRef& r, bool x0_prev, double& bi, double& ax0) {
+  int dummy = 0;
+  const int p = (int)__ldg(a.pat + r.row);
+  const bool in_dict = p != 255;
+  const int base = in_dict ? p * kChunk : 0;
+  const int width = in_dict ? D.sW[p] : r.width;
+  auto col = [&](int k) { return in_dict ? (int32_t)r.row + D.sOff[base + k] : __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); };
+  auto val = [&](int m, int k) {
+    return in_dict ? (m == 0 ? D.sB : D.sA)[base + k] : __ldg((m == 0 ? a.B : a.A) + r.beg + (int64_t)k * kSlice + r.lane);
+  };
+  if (x0_prev) {
+    double ab[2];
+    sell_row<2, false, false, false, false>(width, col, val, a.v_prev, 0, &dummy, 0, ab);
+    bi = ab[0];
+    ax0 = ab[1];
+  } else {
+    double b1[1];
+    sell_row<1, false, false, false, false>(width, col, val, a.v_prev, 0, &dummy, 0, b1);
+    bi = b1[0];
+    ax0 = 0.0;
+  }
+  if (a.has_stim) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
+}
+
 __device__ __forceinline__ double norm_term(int norm_type, double r, double z) {
   // summand of the squared residual norm: preconditioned ||M^-1 r||, unpreconditioned ||r||, natural r.M^-1 r
   return norm_type == MONO_NORM_PRECONDITIONED ? z * z : (norm_type == MONO_NORM_UNPRECONDITIONED ? r * r : r * z);
@@ -736,8 +812,9 @@ __device__ __forceinline__ void stage_wait() {
 
 // ---- KSPCG (PETSc semantics): two reductions per iteration ------------------------------------------------
 //   q = A p ; alpha = (r,z)/(p,q) ; x += alpha p ; r -= alpha q ; z = M^-1 r ; beta = (r,z)_new/(r,z) ; p = z + beta p
-template <bool RESIDENT, bool MATSMEM, bool MULTI>
+template <bool RESIDENT, bool MATSMEM, bool MULTI, bool DICT = false>
 __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a) {
+  static_assert(!DICT || (!RESIDENT && !MATSMEM), "the stencil dictionary serves the streaming mode");
   extern __shared__ double dyn_smem[];
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
@@ -758,7 +835,9 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
   const int width_cached = stage_matrix<MATSMEM>(a, sa, sc, warp_global, lane);
   const MatA<MATSMEM, false> Aop{a, sa, sc};
   Stager S{};
-  if constexpr (!RESIDENT) {
+  [[maybe_unused]] DictView D{};
+  if constexpr (DICT) D = dict_load(a, dyn_smem);  // (the dictionary takes the place of the stage buffers: a.staged is 0)
+  if constexpr (!RESIDENT && !DICT) {
     if (a.staged) {  // (block-uniform) per-warp stage buffers + mbarriers in the otherwise unused dynamic shared memory
       const int warp = threadIdx.x >> 5;
       char* smem = reinterpret_cast<char*>(dyn_smem);
@@ -794,7 +873,17 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     acc3[2] += norm_term(a.norm_type, bi, di * bi);
   };
   bool rhs_staged = false;
-  if constexpr (!RESIDENT) {
+  if constexpr (DICT) {
+    rhs_staged = true;
+    OWN_ROWS_BEGIN
+      if (r.row < a.n_owned) {
+        double bi, ax0;
+        dict_rhs_row(a, D, r, x0_prev, bi, ax0);
+        rhs_finish(r, bi, ax0);
+      }
+    OWN_ROWS_END
+  }
+  if constexpr (!RESIDENT && !DICT) {
     if (a.staged && !x0_prev) {  // b = B v_ with the B slices arriving through the stage buffers
       rhs_staged = true;
       if (lane == 0) {
@@ -842,7 +931,18 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     // ---- K4a: q = A p (gathers wait on the tag of each element), p.q ----------------------------------------
     double pq[1] = {0.0};
     bool staged_done = false;
-    if constexpr (!RESIDENT) {
+    if constexpr (DICT) {
+      staged_done = true;
+      OWN_ROWS_BEGIN
+        if (r.row < a.n_owned) {
+          const double pi = __ldcg(a.work[VP] + r.row);  // requested before the gathers
+          const double qi = dict_apply<MULTI>(a, D, r, a.tb[cur], vtag, &sh.fail);
+          __stcg(a.work[VQ] + r.row, qi);
+          pq[0] = fma(pi, qi, pq[0]);
+        }
+      OWN_ROWS_END
+    }
+    if constexpr (!RESIDENT && !DICT) {
       if (a.staged) {
         staged_done = true;
         if (lane == 0) {
@@ -1168,6 +1268,16 @@ __global__ void build_ab_kernel(int64_t nnz, const double* __restrict__ mass, co
 
 // also: *gersh = max_i sum_j |a_ij| / a_ii, the Gershgorin bound of the spectrum of D^-1 A (upper end of the
 // Chebyshev interval; positive doubles order like their bit patterns, so an integer atomicMax does it)
+// dictionary values = the A / B entries of each pattern's representative row (same bits as the SELL arrays hold)
+__global__ void dict_gather_kernel(int n, const int64_t* __restrict__ src, const double* __restrict__ A, const double* __restrict__ B,
+                                   double* __restrict__ dA, double* __restrict__ dB) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int64_t e = src[i];
+    dA[i] = e >= 0 ? A[e] : 0.0;
+    dB[i] = e >= 0 ? B[e] : 0.0;
+  }
+}
+
 __global__ void jacobi_kernel(int64_t n_owned, int64_t n_slices, const int64_t* __restrict__ slice_ptr,
                               const int32_t* __restrict__ cols, const double* __restrict__ A,
                               double* __restrict__ dinv, int pc_type, unsigned long long* __restrict__ gersh) {
@@ -1217,6 +1327,60 @@ __global__ void probes_kernel(int n_probes, const ProbeDev* __restrict__ probes,
 }
 
 }  // namespace
+
+// EXPERIMENTAL (MONO_PDE_DICT=1): stencil dictionary of the matrices, see dict_apply.  Keeps the kMaxPat most frequent
+// stencils of at most kChunk entries; the dictionary is used when it covers at least half of the rows.
+static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_t* indices, const double* mass, const double* stiff,
+                                const std::vector<int64_t>& sp) {
+  const int64_t n = c->n_owned;
+  std::vector<uint8_t> pat((size_t)n);
+  int32_t npat = 0;
+  int64_t rep[kMaxPat], cnt[kMaxPat];
+  if (mono_csr_row_patterns(n, indptr, indices, mass, stiff, kMaxPat, pat.data(), &npat, rep, cnt) != MONO_OK)
+    return mono_fail(c, MONO_E_INVALID, std::string("stencil dictionary: ") + mono_last_error(nullptr));
+  // drop patterns wider than one batch of sell_row and renumber
+  int remap[256];
+  for (int i = 0; i < 256; ++i) remap[i] = 255;
+  std::vector<int64_t> krep;
+  int64_t covered = 0;
+  for (int p = 0; p < npat; ++p) {
+    if (indptr[rep[p] + 1] - indptr[rep[p]] > kChunk) continue;
+    remap[p] = (int)krep.size();
+    krep.push_back(rep[p]);
+    covered += cnt[p];
+  }
+  c->dict_cover = (double)covered / (double)n;
+  if (krep.empty() || c->dict_cover < 0.5) {
+    c->n_pat = 0;
+    return MONO_OK;
+  }
+  for (int64_t r = 0; r < n; ++r) pat[(size_t)r] = (uint8_t)remap[pat[(size_t)r]];
+  const int np = (int)krep.size();
+  std::vector<int32_t> off((size_t)np * kChunk, 0), w((size_t)np, 0);
+  std::vector<int64_t> src((size_t)np * kChunk, -1);
+  for (int p = 0; p < np; ++p) {
+    const int64_t r = krep[(size_t)p];
+    const int wd = (int)(indptr[r + 1] - indptr[r]);
+    w[(size_t)p] = wd;
+    for (int k = 0; k < wd; ++k) {
+      off[(size_t)p * kChunk + k] = indices[indptr[r] + k] - (int32_t)r;
+      src[(size_t)p * kChunk + k] = sp[(size_t)(r / kSlice)] + (int64_t)k * kSlice + (r % kSlice);
+    }
+  }
+  MONO_CUDA(c, cudaMalloc(&c->pat_dev, (size_t)n));
+  MONO_CUDA(c, cudaMalloc(&c->dict_off_dev, off.size() * sizeof(int32_t)));
+  MONO_CUDA(c, cudaMalloc(&c->dict_w_dev, w.size() * sizeof(int32_t)));
+  MONO_CUDA(c, cudaMalloc(&c->dict_src_dev, src.size() * sizeof(int64_t)));
+  MONO_CUDA(c, cudaMalloc(&c->dict_A_dev, off.size() * sizeof(double)));
+  MONO_CUDA(c, cudaMalloc(&c->dict_B_dev, off.size() * sizeof(double)));
+  MONO_CUDA(c, cudaMemcpyAsync(c->pat_dev, pat.data(), (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaMemcpyAsync(c->dict_off_dev, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaMemcpyAsync(c->dict_w_dev, w.data(), w.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaMemcpyAsync(c->dict_src_dev, src.data(), src.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->n_pat = np;
+  return MONO_OK;
+}
 
 int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, const double* mass, const double* stiff) {
   const int64_t n = c->n_owned;
@@ -1270,6 +1434,7 @@ int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, c
   MONO_CUDA(c, cudaMemcpyAsync(c->mass, hm.data(), tot * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaMemcpyAsync(c->stiff, hk.data(), tot * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (getenv("MONO_PDE_DICT") != nullptr && n > 0) return pde_build_dictionary(c, indptr, indices, mass, stiff, sp);
   return MONO_OK;
 }
 
@@ -1287,6 +1452,10 @@ int pde_update_matrices(mono_ctx* c, double dt) {
                                                              c->dinv, c->pc_type == MONO_PC_CHEBYSHEV ? MONO_PC_JACOBI : c->pc_type,
                                                              c->gen_state + 2);
     c->launches++;
+    if (c->n_pat > 0) {
+      dict_gather_kernel<<<1, 1024, 0, c->stream>>>(c->n_pat * kChunk, c->dict_src_dev, c->A, c->B, c->dict_A_dev, c->dict_B_dev);
+      c->launches++;
+    }
     MONO_CUDA(c, cudaGetLastError());
   }
   if (c->pc_type == MONO_PC_CHEBYSHEV) {
@@ -1409,7 +1578,15 @@ static int pde_select_mode(mono_ctx* c) {
       c->resident_smem = 0;
     }
   }
-  if (!c->resident && !pipe && c->max_width <= kChunk && getenv("MONO_PDE_NO_STAGING") == nullptr) {
+  c->dict_active = !c->resident && !pipe && c->n_pat > 0;
+  if (c->dict_active) {
+    k = multi ? (const void*)pde_cg_kernel<false, false, true, true> : (const void*)pde_cg_kernel<false, false, false, true>;
+    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kDictSmem) != cudaSuccess) {
+      (void)cudaGetLastError();
+      c->dict_active = false;
+    }
+  }
+  if (!c->dict_active && !c->resident && !pipe && c->max_width <= kChunk && getenv("MONO_PDE_NO_STAGING") == nullptr) {
     k = pde_kernel_for_mode(c, false, false, multi);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmem) == cudaSuccess)
       c->staged = true;
@@ -1513,13 +1690,23 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   fill_sync_args(c, a);
   a.res = c->ksp_dev;
   a.timeline = c->timeline_dev;
+  a.pat = c->pat_dev;
+  a.dict_A = c->dict_A_dev;
+  a.dict_B = c->dict_B_dev;
+  a.dict_off = c->dict_off_dev;
+  a.dict_w = c->dict_w_dev;
+  a.n_pat = c->n_pat;
   const bool multi = c->nranks > 1;
   if (multi && !c->peers_ready)
     return mono_fail(c, MONO_E_INVALID, "multi-rank context: call mono_set_halo (on every rank) before stepping the PDE stage");
   void* args[] = {&a};
-  MONO_CUDA(c, cudaLaunchCooperativeKernel(pde_kernel_for_mode(c, c->resident, c->matsmem, multi),
-                                           dim3(c->pde_blocks), dim3(c->pde_threads), args,
-                                           a.staged ? (size_t)kStagedSmem : c->resident_smem, c->stream));
+  const void* kern = pde_kernel_for_mode(c, c->resident, c->matsmem, multi);
+  size_t smem = a.staged ? (size_t)kStagedSmem : c->resident_smem;
+  if (c->dict_active) {
+    kern = multi ? (const void*)pde_cg_kernel<false, false, true, true> : (const void*)pde_cg_kernel<false, false, false, true>;
+    smem = kDictSmem;
+  }
+  MONO_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(c->pde_blocks), dim3(c->pde_threads), args, smem, c->stream));
   c->launches++;
   return MONO_OK;
 }

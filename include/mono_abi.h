@@ -178,6 +178,11 @@ int mono_ksp_info(mono_ctx *ctx, int *iterations, double *residual_norm, int *re
 /* sum of iterations over all solves since the context was created (no per-step sync needed) */
 int mono_ksp_total_iterations(mono_ctx *ctx, int64_t *total, int64_t *solves);
 
+/* EXPERIMENTAL - stencil dictionary of the matrices (set MONO_PDE_DICT=1 in the environment before
+ * mono_pde_set_matrices): what it found (patterns kept, fraction of owned rows they cover) and whether the solver mode
+ * chosen at the last step uses it (streaming KSPCG only).  Results are bit-identical with and without it. */
+int mono_pde_dictionary_info(mono_ctx *ctx, int *n_patterns, double *rows_covered, int *active);
+
 /* ---- the fused path: MonodomainSplittingSolver.step (monodomain_solver.py:53-116) -------------- */
 /* One operator-split step on the device: ODE(theta_split*dt) -> PDE(dt) [-> ODE((1-theta_split)*dt)],
  * with the v_ode/v_pde/v_ hand-offs of :72-97 fused away.  Post-condition (as after the reference's

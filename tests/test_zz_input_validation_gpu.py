@@ -53,3 +53,42 @@ def test_stimulus_and_probe_indices_are_validated(ctx_factory):
         ctx.probe_add(np.array([n], dtype=np.int32), np.array([1.0]))
     with pytest.raises(MonoError, match="theta"):
         ctx.pde_config(1.0, 1.5, 1e-5, 1e-50, 100, 1, 0, 0)
+
+
+@pytest.mark.parametrize("x0", [0, 1])
+def test_stencil_dictionary_is_bit_identical(ctx_factory, monkeypatch, x0):
+    """EXPERIMENTAL path (MONO_PDE_DICT=1): dictionary rows take their matrix entries from shared memory; same entries,
+    same order, so the solve must reproduce the SELL-streaming kernel bit for bit (iterate, iteration count, norm)."""
+    from beat_b200 import fem
+
+    mesh = fem.create_box(fem.COMM_SELF, [np.zeros(3), np.array([20.0, 7.0, 3.0])], [40, 14, 6])
+    indptr, indices, mass, stiff = fem.assemble_p1_local(mesh, np.diag([0.1334, 0.0176, 0.0176]))
+    n = indptr.size - 1
+    rng = np.random.default_rng(11)
+    v_prev = -85.0 + 120.0 * rng.random(n)
+    stim_idx = np.arange(0, 50, dtype=np.int32)
+    monkeypatch.setenv("MONO_PDE_STREAM", "1")  # force the streaming mode on this small mesh
+    out = {}
+    for label in ("sell", "dict"):
+        if label == "dict":
+            monkeypatch.setenv("MONO_PDE_DICT", "1")
+        else:
+            monkeypatch.delenv("MONO_PDE_DICT", raising=False)
+        ctx = ctx_factory()
+        ctx.pde_set_matrices(n, 0, indptr, indices, mass, stiff)
+        ctx.pde_config(1.0, 0.5, 1e-10, 1e-50, 200, 1, 0, x0)
+        ctx.pde_set_ksp_type(0)
+        ctx.stim_add(stim_idx, np.full(50, 0.01), 0.0, 2.0, 50.0)
+        ctx.set_v_prev(v_prev)
+        ctx.pde_step(0.0, 0.05)
+        x1 = ctx.get_v(np.empty(n))
+        its1, rnorm1, reason1 = ctx.ksp_info()
+        ctx.set_v_prev(x1)
+        ctx.pde_step(0.05, 0.15)  # dt changes: A, B and the dictionary values are rebuilt
+        out[label] = (x1, ctx.get_v(np.empty(n)), its1, rnorm1, reason1, ctx.ksp_info(), ctx.pde_dictionary_info())
+    assert out["sell"][6] == {"patterns": 0, "rows_covered": 0.0, "active": False}
+    info = out["dict"][6]
+    assert info["patterns"] == 27 and info["rows_covered"] == 1.0 and info["active"]
+    assert out["sell"][4] > 0 and out["sell"][2] > 3
+    for a, b in zip(out["sell"][:6], out["dict"][:6]):
+        assert np.array_equal(np.asarray(a), np.asarray(b))

@@ -103,3 +103,24 @@ def test_shell_mesh_matches_generic_builder(n, size):
         assert np.array_equal(fa, fb)
         marker = lambda x: x[0] > 2.0  # noqa: E731
         assert np.array_equal(fem.locate_entities(a, 3, marker), fem.locate_entities(b, 3, marker))
+
+
+@pytest.mark.parametrize("size", [2, 3, 8])
+def test_halo_lists_satisfy_the_abi_preconditions(size):
+    """What mono_set_halo validates (csrc/halo.cu): pointers start at 0, are non-decreasing, cover exactly the ghost block;
+    send indices are owned dofs; neighbours are other ranks; everything int32 - for every mesh builder."""
+    for rank in range(size):
+        comm = fem.Comm(rank, size)
+        box = [np.zeros(3), np.array([20.0, 7.0, 3.0])]
+        meshes = {"box": fem.create_box(comm, box, [40, 14, 6]), "box_generic": fem._create_box_generic(comm, box, [16, 6, 4]),
+                  "shell": fem.create_lv_ellipsoid(comm, 2, 6, 24), "rectangle": fem.create_rectangle(comm, ((0, 0), (1, 1)), (16, 8)),
+                  "interval": fem.create_interval(comm, 64, (0.0, 1.0))}
+        for what, mesh in meshes.items():
+            im = mesh.index_map
+            sp, rp, nbr, si = im.send_ptr, im.recv_ptr, im.nbr_ranks, im.send_idx
+            assert len(sp) == len(nbr) + 1 == len(rp), what
+            assert sp[0] == 0 and rp[0] == 0 and (np.diff(sp) >= 0).all() and (np.diff(rp) >= 0).all(), what
+            assert rp[-1] == im.num_ghosts and len(si) == sp[-1], what
+            assert (si >= 0).all() and (si < im.size_local).all(), what
+            assert all(0 <= q < size and q != rank for q in nbr), what
+            assert all(a.dtype == np.int32 for a in (sp, rp, nbr, si)), what

@@ -6,8 +6,6 @@ carry TP06 (the BASELINE config names TP06) with g_Ks / g_to scaled per layer as
 
 from __future__ import annotations
 
-import numpy as np
-
 from . import conductivities, fem, geometry, stimulation
 from .models import tp06
 from .monodomain_model import MonodomainModel

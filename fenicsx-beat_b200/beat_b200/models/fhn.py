@@ -2,8 +2,6 @@
 
 The step functions are *device handles*: they name a CUDA kernel, they are not callable on the CPU.
 """
-import math
-
 import numpy as np
 
 from ..device_model import DeviceODE

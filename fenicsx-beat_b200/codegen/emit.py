@@ -356,4 +356,7 @@ def emit_host_module(progs: list[Program], model_tag: str, model_id: int) -> str
             f"derived=_derived_{short}, op_counts={c!r})"
         )
     lines.append("")
+    if not any("math." in ln for ln in lines):  # (models whose hoisted constants need no transcendental function)
+        at = lines.index("import math")
+        del lines[at: at + 2]
     return "\n".join(lines)

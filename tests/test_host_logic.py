@@ -97,3 +97,21 @@ def test_conductivities():  # src/beat/conductivities.py:29-118
     assert np.allclose(M2 @ f, s_l * f) and np.allclose(M2, M2.T)
     with pytest.raises(ValueError):
         conductivities.default_conductivities("nobody")
+
+
+def test_single_cell_cache_and_type_check(tmp_path):
+    """get_steady_state (reference src/beat/single_cell.py:86-156): Python callables are refused (no CPU fallback), the
+    cache key depends on every input, and a cached result is returned without touching the device."""
+    from beat_b200 import single_cell
+    from beat_b200.models import tp06
+
+    y0, p = tp06.init_state_values(), tp06.init_parameter_values()
+    with pytest.raises(TypeError, match="device model handle"):
+        single_cell.get_steady_state(lambda **kw: kw["states"], y0, p, tmp_path)
+    fun = tp06.generalized_rush_larsen
+    key = single_cell.compute_hash(fun, y0, p, 200, 1000, 0.05)
+    assert key != single_cell.compute_hash(fun, y0, tp06.init_parameter_values(g_Ks=0.1), 200, 1000, 0.05)
+    assert key != single_cell.compute_hash(tp06.forward_explicit_euler, y0, p, 200, 1000, 0.05)
+    assert key != single_cell.compute_hash(fun, y0, p, 100, 1000, 0.05)
+    np.save(tmp_path / f"steady_states_{key}.npy", np.arange(len(y0), dtype=float))
+    assert np.array_equal(single_cell.get_steady_state(fun, y0, p, tmp_path), np.arange(len(y0)))

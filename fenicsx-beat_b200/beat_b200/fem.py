@@ -1223,16 +1223,35 @@ def point_probe(mesh: Mesh, point: Sequence[float]):
     d = mesh.topology.dim
     p = np.asarray(point, dtype=np.float64)[:d]
     X = mesh.geometry.x[:, :d]
-    cx = X[mesh.cells]  # (ncell, d+1, d)
-    lo, hi = cx.min(axis=1), cx.max(axis=1)
-    cand = np.nonzero(np.all((p >= lo - 1e-12) & (p <= hi + 1e-12), axis=1))[0]
+    if isinstance(mesh, BoxMesh):
+        # candidates by index arithmetic: the Kuhn tets of the (at most 8) cubes around the point that are local -
+        # a 10^7-dof rank must not materialise its 6 x 10^7 cells for nine probes
+        rel = [(p[k] - mesh.p0[k]) / mesh.h[k] for k in range(3)]
+        if any(r < -1e-9 or r > mesh.n[k] + 1e-9 for k, r in enumerate(rel)):
+            return None
+        spans = []
+        for k, r in enumerate(rel):
+            base = int(np.floor(r + 1e-9))
+            lo_c, hi_c = (mesh.c0, mesh.c1 - 1) if k == 0 else (0, mesh.n[k] - 1)
+            spans.append([c for c in {base - 1, base} if lo_c <= c <= hi_c and abs(r - np.clip(r, c, c + 1)) <= 1e-9])
+        w_, ncube = mesh.c1 - mesh.c0, mesh.num_cubes
+        cubes = [(k_ * mesh.n[1] + j_) * w_ + (i_ - mesh.c0) for i_ in spans[0] for j_ in spans[1] for k_ in spans[2]]
+        cand_ids = np.sort(np.array([q * ncube + c for c in cubes for q in range(6)], dtype=np.int64))
+        cand_cells = mesh.cells_of(cand_ids) if cand_ids.size else np.zeros((0, 4), dtype=np.int64)
+    else:
+        cells = mesh.cells
+        cxa = X[cells]  # (ncell, d+1, d)
+        lo, hi = cxa.min(axis=1), cxa.max(axis=1)
+        cand_ids = np.nonzero(np.all((p >= lo - 1e-12) & (p <= hi + 1e-12), axis=1))[0]
+        cand_cells = cells[cand_ids]
     best = None
-    for c in cand:
-        T = (cx[c, 1:] - cx[c, 0]).T
-        lam = np.linalg.solve(T, p - cx[c, 0])
+    for verts in cand_cells:  # (in cell order: ties go to the lowest cell id on both routes)
+        cx = X[verts]
+        T = (cx[1:] - cx[0]).T
+        lam = np.linalg.solve(T, p - cx[0])
         w = np.concatenate([[1.0 - lam.sum()], lam])
         if w.min() >= -1e-10 and (best is None or w.min() > best[1].min()):
-            best = (mesh.cells[c].astype(np.int32), w)
+            best = (verts.astype(np.int32), w)
     if best is None:
         return None
     nodes, w = best

@@ -124,3 +124,22 @@ def test_halo_lists_satisfy_the_abi_preconditions(size):
             assert (si >= 0).all() and (si < im.size_local).all(), what
             assert all(0 <= q < size and q != rank for q in nbr), what
             assert all(a.dtype == np.int32 for a in (sp, rp, nbr, si)), what
+
+
+@pytest.mark.parametrize("size", [1, 3])
+def test_point_probe_by_index_arithmetic_matches_the_cell_search(size):
+    """fem.point_probe on a BoxMesh looks only at the cubes around the point; same cell, same weights as the search over
+    all cells of the generic mesh - for the Niederer probe points, points on faces / edges, random and outside points."""
+    rng = np.random.default_rng(0)
+    pts = [(0, 0, 0), (0, 7, 0), (20, 0, 0), (20, 7, 0), (0, 0, 3), (0, 7, 3), (20, 0, 3), (20, 7, 3), (10, 3.5, 1.5), (9.99999, 3.5, 1.5),
+           (10.0, 3.4, 1.5), (5.0, 0.0, 1.25), (25, 1, 1), (-0.1, 0, 0)] + [tuple(rng.random(3) * [20, 7, 3]) for _ in range(40)]
+    box = [np.zeros(3), np.array([20.0, 7.0, 3.0])]
+    for rank in range(size):
+        comm = fem.Comm(rank, size)
+        a, b = fem.create_box(comm, box, [40, 14, 6]), fem._create_box_generic(comm, box, [40, 14, 6])
+        for pt in pts:
+            ha, hb = fem.point_probe(a, pt), fem.point_probe(b, pt)
+            assert (ha is None) == (hb is None), (pt, rank)
+            if ha is not None:
+                assert np.array_equal(ha[0], hb[0]) and np.allclose(ha[1], hb[1], atol=1e-12), (pt, rank)
+                assert np.allclose(a.geometry.x[ha[0]].T @ ha[1], pt, atol=1e-9)

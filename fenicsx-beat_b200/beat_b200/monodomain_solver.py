@@ -24,15 +24,14 @@ EPS = 1e-12
 
 
 class ODESolver(Protocol):
-    def to_dolfin(self) -> None: ...
-
-    def from_dolfin(self) -> None: ...
-
-    def ode_to_pde(self) -> None: ...
-
-    def pde_to_ode(self) -> None: ...
+    """What the splitting solver needs from an ODE backend (monodomain_solver.py:14-23): advance the cell states, and
+    move the membrane potential between the state array, its function in the ODE space and the PDE space."""
 
     def step(self, t0: float, dt: float) -> None: ...
+    def to_dolfin(self) -> None: ...          # states[v_index] -> v_ode
+    def from_dolfin(self) -> None: ...        # v_ode -> states[v_index]
+    def ode_to_pde(self) -> None: ...         # v_ode -> v_pde
+    def pde_to_ode(self) -> None: ...         # v_pde -> v_ode
 
 
 @dataclass
@@ -51,16 +50,15 @@ class MonodomainSplittingSolver:
         if self._fused and self._timed:
             self.pde._ctx.stage_timing(True)
 
-    def solve(self, interval, dt):  # monodomain_solver.py:39-51
-        T0, T = interval
-        if dt is None:
-            dt = T - T0
-        t0 = T0
-        t1 = T0 + dt
-        while t1 < T + EPS:
-            self.step((t0, t1))
-            t0 = t1
-            t1 = t0 + dt
+    def solve(self, interval, dt=None):  # monodomain_solver.py:39-51
+        """Fixed-size steps over ``interval``; a step is taken while its END does not pass T (+1e-12), and every end time
+        is previous end + dt (the reference's accumulation, so the same number of steps comes out)."""
+        begin, end = interval
+        width = (end - begin) if dt is None else dt
+        left = begin
+        while (right := left + width) < end + EPS:
+            self.step((left, right))
+            left = right
 
     def _prepare_fused(self, t0: float, t1: float) -> None:
         pde, ode = self.pde, self.ode
@@ -108,35 +106,29 @@ class MonodomainSplittingSolver:
         self._mark_fused()
 
     def _step_protocol(self, interval):
-        theta = self.theta
+        """Any other ODE backend (the 5-method ODESolver protocol): the hand-offs of the reference's step, one timed label
+        each (monodomain_solver.py:66-113), as data - first half, then either the Godunov or the Strang tail."""
         t0, t1 = interval
         dt = t1 - t0
-        t = t0 + theta * dt
+        ode, pde, theta = self.ode, self.pde, self.theta
+        godunov = bool(np.isclose(theta, 1.0))
+        first_half = (
+            ("ode_step", lambda: ode.step(t0=t0, dt=theta * dt)),
+            ("ode_to_dolfin", ode.to_dolfin),
+            ("ode_to_pde", ode.ode_to_pde),
+            ("pde_assign_previous_before", pde.assign_previous),
+            ("pde_step", lambda: pde.step((t0, t1))),
+            ("pde_to_ode", ode.pde_to_ode),
+            ("ode_from_dolfin", ode.from_dolfin),
+        )
+        tail = (("pde_assign_previous_after", pde.assign_previous),) if godunov else (
+            ("corrective_ode_step", lambda: ode.step(t0 + theta * dt, (1.0 - theta) * dt)),
+            ("corrective_ode_to_dolfin", ode.to_dolfin),
+            ("corrective_ode_to_pde", ode.ode_to_pde),
+            ("corrective_pde_assign_previous", pde.assign_previous),
+        )
         with self.monitor.track_time("total_step"):
-            with self.monitor.track_time("ode_step"):
-                self.ode.step(t0=t0, dt=theta * dt)
-            with self.monitor.track_time("ode_to_dolfin"):
-                self.ode.to_dolfin()
-            with self.monitor.track_time("ode_to_pde"):
-                self.ode.ode_to_pde()
-            with self.monitor.track_time("pde_assign_previous_before"):
-                self.pde.assign_previous()
-            with self.monitor.track_time("pde_step"):
-                self.pde.step((t0, t1))
-            with self.monitor.track_time("pde_to_ode"):
-                self.ode.pde_to_ode()
-            with self.monitor.track_time("ode_from_dolfin"):
-                self.ode.from_dolfin()
-            if np.isclose(theta, 1.0):
-                with self.monitor.track_time("pde_assign_previous_after"):
-                    self.pde.assign_previous()
-            else:
-                with self.monitor.track_time("corrective_ode_step"):
-                    self.ode.step(t, (1.0 - theta) * dt)
-                with self.monitor.track_time("corrective_ode_to_dolfin"):
-                    self.ode.to_dolfin()
-                with self.monitor.track_time("corrective_ode_to_pde"):
-                    self.ode.ode_to_pde()
-                with self.monitor.track_time("corrective_pde_assign_previous"):
-                    self.pde.assign_previous()
+            for label, action in first_half + tail:
+                with self.monitor.track_time(label):
+                    action()
         self.monitor.advance_step(t0, t1)

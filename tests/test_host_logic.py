@@ -115,3 +115,87 @@ def test_single_cell_cache_and_type_check(tmp_path):
     assert key != single_cell.compute_hash(fun, y0, p, 100, 1000, 0.05)
     np.save(tmp_path / f"steady_states_{key}.npy", np.arange(len(y0), dtype=float))
     assert np.array_equal(single_cell.get_steady_state(fun, y0, p, tmp_path), np.arange(len(y0)))
+
+
+def test_performance_monitor_log_line_summary_and_device_labels(tmp_path, caplog):
+    """The tokens the reference's tests look for (tests/test_telemetry.py:72-146) plus the device ledger: a label timed
+    with CUDA events replaces the host interval of the same name."""
+    m = telemetry.PerformanceMonitor(log_frequency=2)
+    m.timings["step_time"] = 0.5
+    with caplog.at_level(logging.INFO):
+        m.advance_step(0.0, 0.1)
+        assert len(caplog.records) == 0
+        m.advance_step(0.1, 0.2)
+    assert len(caplog.records) == 1
+    msg = caplog.records[0].message
+    assert "PDE step timing step=2" in msg and "step_time=" in msg and "ksp_iterations=0" in msg
+    caplog.clear()
+    m.timings.update({"slow_op": 10.0, "fast_op": 1.0})
+    with m.track_time("pde_step"):
+        pass
+    m.record_device_stages({"pde_step": 0.25})
+    m.record_device_stages({"pde_step": 0.25})
+    assert m.timings["pde_step"] == 0.5  # host interval dropped, device totals accumulate
+    with m.track_time("pde_step"):
+        pass
+    assert m.timings["pde_step"] == 0.5
+    with caplog.at_level(logging.INFO):
+        m.display_summary()
+    text = caplog.records[0].message
+    assert "PERFORMANCE SUMMARY" in text and "Total Steps:           2" in text and "pde_step [device]" in text
+    assert text.find("slow_op") < text.find("fast_op")
+    out = tmp_path / "sub" / "summary.json"
+    m.save_summary(out)
+    data = json.loads(out.read_text())
+    assert data["total_steps"] == 2 and data["timings"]["slow_op"] == 10.0 and data["device_timed"] == ["pde_step"]
+    other = telemetry.PerformanceMonitor(comm=fem.Comm(1, 2))
+    other.save_summary(tmp_path / "rank1.json")
+    assert not (tmp_path / "rank1.json").exists()
+
+
+@pytest.mark.parametrize("theta", [1.0, 0.5])
+def test_splitting_solver_protocol_sequence(theta):
+    """A non-device ODE backend goes through the reference's hand-off sequence (monodomain_solver.py:33-37,66-113):
+    same calls, same order, same time arguments, one monitor label each."""
+    from beat_b200.monodomain_solver import MonodomainSplittingSolver
+
+    calls = []
+
+    class Ode:
+        def step(self, t0, dt):
+            calls.append(("ode.step", round(t0, 12), round(dt, 12)))
+
+        def to_dolfin(self):
+            calls.append("to_dolfin")
+
+        def from_dolfin(self):
+            calls.append("from_dolfin")
+
+        def ode_to_pde(self):
+            calls.append("ode_to_pde")
+
+        def pde_to_ode(self):
+            calls.append("pde_to_ode")
+
+    class Pde:
+        _ctx = object()
+
+        def assign_previous(self):
+            calls.append("assign_previous")
+
+        def step(self, interval):
+            calls.append(("pde.step", interval))
+
+    mon = telemetry.PerformanceMonitor(log_frequency=0)
+    solver = MonodomainSplittingSolver(pde=Pde(), ode=Ode(), theta=theta, monitor=mon)
+    assert calls == ["to_dolfin", "ode_to_pde", "assign_previous"]
+    calls.clear()
+    solver.solve((0.0, 0.2), 0.1)
+    half = [("ode.step", 0.0, round(theta * 0.1, 12)), "to_dolfin", "ode_to_pde", "assign_previous", ("pde.step", (0.0, 0.1)), "pde_to_ode",
+            "from_dolfin"]
+    tail = ["assign_previous"] if theta == 1.0 else [("ode.step", 0.05, 0.05), "to_dolfin", "ode_to_pde", "assign_previous"]
+    assert calls[: len(half) + len(tail)] == half + tail
+    assert len(calls) == 2 * (len(half) + len(tail)) and mon.step_counter == 2
+    labels = set(mon.timings)
+    assert {"total_step", "ode_step", "pde_step", "ode_from_dolfin"} <= labels
+    assert ("pde_assign_previous_after" in labels) == (theta == 1.0) and ("corrective_ode_step" in labels) == (theta != 1.0)

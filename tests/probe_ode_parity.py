@@ -1,6 +1,7 @@
-"""Per-state single-step parity of the device GRL1 kernels against the NumPy oracle on 20 000 random states (prints the worst states)."""
+"""TEST INFRASTRUCTURE (uses the oracle): per-state single-step parity of the device GRL1 kernels against the NumPy oracle on
+20 000 random states, printing the worst states.  Run from the repository root: python tests/probe_ode_parity.py [t0]"""
 import sys, importlib
-sys.path.insert(0, "fenicsx-beat_b200"); sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+sys.path.insert(0, "fenicsx-beat_b200"); sys.path.insert(0, ".")
 import numpy as np
 import _problems as P
 from beat_b200._lib import Context

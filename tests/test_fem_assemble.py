@@ -82,3 +82,44 @@ def test_library_assembler_reports_bad_input():
                                   buf_i.ctypes.data_as(C.POINTER(C.c_int32)), buf_m.ctypes.data_as(C.POINTER(C.c_double)),
                                   buf_k.ctypes.data_as(C.POINTER(C.c_double)))
     assert rc == -1 and b"indptr" in lib.mono_last_error(None)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_library_assembler_on_delaunay_meshes(dim):
+    """Genuinely unstructured connectivity (SciPy Delaunay of random points, irregular vertex degrees up to ~40): owned
+    rows only, cell-wise tensor - against the dense accumulation of the element matrices."""
+    from scipy.spatial import Delaunay
+
+    rng = np.random.default_rng(dim)
+    pts = rng.random((300 if dim == 3 else 500, dim))
+    tri = Delaunay(pts)
+    cells = tri.simplices.astype(np.int64)
+    e = pts[cells[:, 1:]] - pts[cells[:, :1]]
+    vol = np.abs(np.linalg.det(e))
+    cells = cells[vol > 1e-9]  # drop slivers on the hull
+    x = np.zeros((pts.shape[0], 3))
+    x[:, :dim] = pts
+    A = rng.standard_normal((cells.shape[0], dim, dim))
+    M = A @ A.transpose(0, 2, 1) + np.eye(dim)
+    n_owned = pts.shape[0] * 2 // 3
+    indptr, indices, mass, stiff = fem_assemble_p1(dim, n_owned, cells, x, M)
+    # dense reference
+    n = pts.shape[0]
+    Md, Kd, pattern = np.zeros((n, n)), np.zeros((n, n)), np.zeros((n, n), dtype=bool)
+    ref = (1.0 + np.eye(dim + 1)) / ((dim + 1) * (dim + 2))
+    fact = 2.0 if dim == 2 else 6.0
+    for c, verts in enumerate(cells):
+        P_ = np.hstack([np.ones((dim + 1, 1)), pts[verts]])
+        G = np.linalg.inv(P_)[1:].T  # rows: gradients of the barycentric coordinates
+        v = abs(np.linalg.det(P_)) / fact
+        Md[np.ix_(verts, verts)] += v * ref
+        Kd[np.ix_(verts, verts)] += v * (G @ M[c] @ G.T)
+        pattern[np.ix_(verts, verts)] = True
+    import scipy.sparse as sp
+
+    got_m = sp.csr_matrix((mass, indices, indptr), shape=(n_owned, n)).toarray()
+    got_k = sp.csr_matrix((stiff, indices, indptr), shape=(n_owned, n)).toarray()
+    assert np.array_equal(np.diff(indptr), pattern[:n_owned].sum(axis=1))
+    assert all(np.all(np.diff(indices[indptr[r]: indptr[r + 1]]) > 0) for r in range(n_owned))  # sorted, no duplicates
+    assert np.abs(got_m - Md[:n_owned]).max() <= 1e-13 * np.abs(Md).max()
+    assert np.abs(got_k - Kd[:n_owned]).max() <= 1e-11 * np.abs(Kd).max()

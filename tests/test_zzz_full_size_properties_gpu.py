@@ -2,7 +2,8 @@
 properties (tests/_properties.py): the diffusion step of the 3.4 M-dof Niederer slab (dx = 0.05 mm) must satisfy its
 own linear system and conserve charge, evaluated on the host with SciPy products only; the cell-model kernel at 1e7
 (TP06) / 1e6 (ToR-ORd) nodes must be pointwise - identical nodes give bit-identical results wherever they sit - and
-agree with the oracle on the distinct ones.  Runs last (several GB of host memory, ~1 min)."""
+agree with the oracle on the distinct ones; a Delaunay mesh with rows twice as wide as a structured mesh has (the shape of
+a real LV mesh) against a sparse LU.  Runs last (several GB of host memory, ~1 min)."""
 
 import importlib
 
@@ -100,3 +101,64 @@ def test_stencil_dictionary_at_3p4M_dofs_is_bit_identical(ctx_factory, slab_005,
     for (xa, ka), (xb, kb) in zip(ref, got):
         assert ka == kb
         assert np.array_equal(xa, xb)
+
+
+def _delaunay_problem():
+    """A genuinely unstructured tetrahedral mesh (SciPy Delaunay of random points): vertex degrees far above the 15 of a
+    Kuhn-split box, so SELL slices are wider than one 16-entry batch - the shape of a real LV mesh (BASELINE config 5)."""
+    from scipy.spatial import Delaunay
+
+    from beat_b200._lib import fem_assemble_p1
+
+    rng = np.random.default_rng(42)
+    pts = rng.random((6000, 3)) * [4.0, 2.0, 1.0]
+    cells = Delaunay(pts).simplices.astype(np.int64)
+    e = pts[cells[:, 1:]] - pts[cells[:, :1]]
+    vol = np.abs(np.linalg.det(e)) / 6.0
+    longest = np.max(np.linalg.norm(pts[cells][:, :, None, :] - pts[cells][:, None, :, :], axis=-1), axis=(1, 2))
+    cells = cells[vol / longest**3 > 5e-3]  # no slivers
+    used = np.unique(cells)
+    renum = np.full(pts.shape[0], -1, dtype=np.int64)
+    renum[used] = np.arange(used.size)
+    pts, cells = pts[used], renum[cells]
+    A = rng.standard_normal((cells.shape[0], 3, 3))
+    M = 2e-3 * (A @ A.transpose(0, 2, 1) + np.eye(3))  # cell-wise anisotropic conductivity
+    indptr, indices, mass, stiff = fem_assemble_p1(3, pts.shape[0], cells, pts, M)
+    return dict(indptr=indptr, indices=indices, mass=mass, stiff=stiff, n=pts.shape[0], pts=pts)
+
+
+@pytest.mark.parametrize("ksp,stream", [(0, False), (1, False), (0, True), (1, True)])
+def test_unstructured_mesh_with_wide_rows(ctx_factory, monkeypatch, ksp, stream):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as sla
+
+    s = _delaunay_problem()
+    n = s["n"]
+    assert np.diff(s["indptr"]).max() > 20  # wider than one batch of the row kernels
+    if stream:
+        monkeypatch.setenv("MONO_PDE_STREAM", "1")
+    else:
+        monkeypatch.delenv("MONO_PDE_STREAM", raising=False)
+    C_m, theta, dt, amp = 0.01, 0.5, 0.02, 0.4
+    rng = np.random.default_rng(8)
+    v_prev = -85.0 + 100.0 * np.exp(-((s["pts"][:, 0] - 1.0) ** 2) / 0.3) + rng.random(n)
+    stim_idx = np.nonzero(s["pts"][:, 0] < 0.4)[0].astype(np.int32)
+    stim_val = np.full(stim_idx.size, 3e-4)
+    ctx = ctx_factory()
+    ctx.pde_set_matrices(n, 0, s["indptr"], s["indices"], s["mass"], s["stiff"])
+    ctx.pde_config(C_m, theta, 1e-11, 1e-50, 2000, 1, 0, 0)  # (condition number 26: ~65 iterations; error <= 26 * 1e-11)
+    ctx.pde_set_ksp_type(ksp)
+    ctx.stim_add(stim_idx, stim_val, 0.0, 1.0, amp)
+    ctx.set_v_prev(v_prev)
+    ctx.pde_step(0.0, dt)
+    x = ctx.get_v(np.empty(n))
+    its, rnorm, reason = ctx.ksp_info()
+    ctx.close()
+    assert reason > 0 and its >= 3, (its, rnorm, reason)
+    Mm = sp.csr_matrix((s["mass"], s["indices"], s["indptr"]), shape=(n, n))
+    K = sp.csr_matrix((s["stiff"], s["indices"], s["indptr"]), shape=(n, n))
+    source = np.zeros(n)
+    source[stim_idx] = amp * stim_val
+    b = (C_m * Mm - (1 - theta) * dt * K) @ v_prev + dt * source
+    want = sla.spsolve((C_m * Mm + theta * dt * K).tocsc(), b)
+    assert np.abs(x - want).max() <= 1e-8 * np.abs(want).max()

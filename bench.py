@@ -54,6 +54,9 @@ LV_WORKLOADS = {
     "lv_ellipsoid_40k": ((6, 48, 128), 0.01),
     "lv_ellipsoid_320k": ((12, 128, 192), 0.01),
     "lv_ellipsoid_1.4M": ((16, 256, 320), 0.01),
+    "lv_ellipsoid_13M": ((24, 256, 2048), 0.01),    # 13.2 M dofs: fits one GPU, the per-GPU share of the 100 M shell
+    "lv_ellipsoid_100M": ((48, 512, 4096), 0.01),   # 103.0 M dofs: BASELINE config 5 at its named size (8 GPUs, --scaling strong;
+                                                    # set-up ~2 min and ~23 GB of host memory per rank)
 }
 
 

@@ -29,3 +29,18 @@ def test_activation_times_dx05_dt005_within_one_dt():
 def test_activation_times_dx05_dt001():
     d = _diff(0.5, 0.01, rtol=1e-10)
     assert np.abs(d).max() <= 0.06, d  # ms: 0.1 % of the arrival times; solver-tolerance residual of the reference
+
+
+def test_activation_times_dx01_dt005_third_published_resolution():
+    """dx = 0.1 (442 k dofs, ~140 s on 8 cores: only with MONO_SLOW_TESTS=1).  Five points within one dt of the published
+    row, the far corners up to 0.15 ms (0.4 %) early, the centre 0.1 ms late - unchanged at rtol 1e-10, i.e. not a
+    solver-tolerance effect on the oracle's side."""
+    import os
+
+    import pytest
+
+    if not os.environ.get("MONO_SLOW_TESTS"):
+        pytest.skip("slow (set MONO_SLOW_TESTS=1)")
+    act = N.run(0.1, 0.05, T=45.0, tp06=P.oracle_model("tp06"))
+    d = np.array([act[k] for k in N.POINTS]) - np.array(N.PUBLISHED[(0.1, 0.05)])
+    assert np.abs(d).max() <= 0.15 + 1e-9 and (np.abs(d) <= 0.05 + 1e-9).sum() >= 5, d

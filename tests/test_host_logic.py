@@ -199,3 +199,41 @@ def test_splitting_solver_protocol_sequence(theta):
     labels = set(mon.timings)
     assert {"total_step", "ode_step", "pde_step", "ode_from_dolfin"} <= labels
     assert ("pde_assign_previous_after" in labels) == (theta == 1.0) and ("corrective_ode_step" in labels) == (theta != 1.0)
+
+
+def test_petsc_options_to_device_solver_settings():
+    """MonodomainModel._solver_settings: how the reference's petsc_options (base_model.py:136-168, demos) select the device
+    solver - checked on a stub, no GPU: preonly/lu = tight CG, unknown preconditioners (hypre, ...) = Jacobi, 'auto' picks
+    the driver by rows per rank and the polynomial preconditioner only for multi-rank resident meshes."""
+    from types import SimpleNamespace
+
+    from beat_b200.monodomain_model import NORM, PC, MonodomainModel
+
+    def settings(opts, n_global=58_176, ranks=1, **params):
+        stub = SimpleNamespace(parameters={"petsc_options": opts, **params},
+                               _ctx=SimpleNamespace(device_info=lambda: {"n_sm": 148}),
+                               _mesh=SimpleNamespace(index_map=SimpleNamespace(size_global=n_global), comm=SimpleNamespace(size=ranks)))
+        out = MonodomainModel._solver_settings(stub)
+        return out, stub
+
+    (rtol, atol, max_it, pc, norm, x0), s = settings({"ksp_type": "preonly", "pc_type": "lu", "pc_factor_mat_solver_type": "mumps"})
+    assert (rtol, pc, norm, x0) == (1e-12, PC["jacobi"], NORM["default"], 0) and s.ksp_type_used == "preonly" and s._ksp_type == 0
+    (rtol, atol, max_it, pc, norm, x0), s = settings({"ksp_type": "cg", "pc_type": "hypre", "pc_hypre_type": "boomeramg"})
+    assert (rtol, atol, max_it, pc) == (1e-5, 1e-50, 10000, PC["jacobi"]) and s.pc_type_used == "jacobi"
+    (rtol, _, max_it, pc, norm, x0), s = settings({"ksp_type": "pipecg", "pc_type": "none", "ksp_rtol": 1e-9, "ksp_max_it": 50,
+                                                   "ksp_norm_type": "unpreconditioned", "ksp_initial_guess_nonzero": True})
+    assert (rtol, max_it, pc, norm, x0) == (1e-9, 50, PC["none"], NORM["unpreconditioned"], 1) and s._ksp_type == 1
+    assert settings({"ksp_type": "cg"}, initial_guess_previous=True)[0][5] == 1
+    # auto: one row per thread on 147 worker CTAs -> pipelined driver; beyond -> KSPCG
+    assert settings({"ksp_type": "auto"}, n_global=147 * 512)[1].ksp_type_used == "pipecg"
+    assert settings({"ksp_type": "auto"}, n_global=147 * 512 + 1)[1].ksp_type_used == "cg"
+    assert settings({"ksp_type": "auto"}, n_global=8 * 58_176, ranks=8)[1].pc_type_used == "chebyshev"       # multi-rank, resident
+    assert settings({"ksp_type": "auto", "pc_type": "jacobi"}, n_global=8 * 58_176, ranks=8)[1].pc_type_used == "jacobi"
+    assert settings({"ksp_type": "auto"}, n_global=58_176, ranks=1)[1].pc_type_used == "jacobi"
+    assert settings({"ksp_type": "auto"}, n_global=27_000_000, ranks=8)[1].pc_type_used == "jacobi"          # streaming: KSPCG
+    (_, _, _, pc, _, _), s = settings({"ksp_type": "pipecg", "pc_type": "chebyshev", "pc_chebyshev_steps": 2, "pc_chebyshev_kappa": 6})
+    assert pc == PC["chebyshev"] and s._cheb == (2, 6.0)
+    with pytest.raises(NotImplementedError, match="pipelined"):
+        settings({"ksp_type": "cg", "pc_type": "chebyshev"})
+    with pytest.raises(NotImplementedError, match="gmres"):
+        settings({"ksp_type": "gmres"})

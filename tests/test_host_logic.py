@@ -237,3 +237,53 @@ def test_petsc_options_to_device_solver_settings():
         settings({"ksp_type": "cg", "pc_type": "chebyshev"})
     with pytest.raises(NotImplementedError, match="gmres"):
         settings({"ksp_type": "gmres"})
+
+
+def test_vector_mirror_coherence_protocol():
+    """fem.Vector: the host mirror of a device vector (what dolfinx's Function.x.array is to the reference).  A fake device
+    counts transfers: lazy download, one upload per modification, read-only views do not dirty, an asynchronous upload is
+    waited for before the buffer is handed out again, and twins (v_ode / v / v_ after a fused step) share one download."""
+    log = []
+    dev = {"a": np.zeros(4), "b": np.zeros(4)}
+
+    def binder(key):
+        def download(out):
+            log.append(("down", key))
+            out[:] = dev[key]
+
+        def upload(src):
+            log.append(("up", key))
+            dev[key] = np.array(src)
+
+        return download, upload
+
+    a, b = fem.Vector(4), fem.Vector(4)
+    a.bind(*binder("a"), push_now=False, sync=lambda: log.append(("sync", "a")))
+    b.bind(*binder("b"), push_now=False, sync=lambda: log.append(("sync", "b")))
+    assert a.array_ro.sum() == 0 and log == []          # nothing newer on the device, nothing to fetch
+    a.flush_to_device()
+    assert log == []                                     # a read-only view did not dirty the mirror
+    a.array[:] = [1, 2, 3, 4]
+    a.flush_to_device()
+    a.flush_to_device()
+    assert log == [("up", "a")] and dev["a"].tolist() == [1, 2, 3, 4]
+    _ = a.array_ro                                       # the upload may still be in flight: wait before exposing the buffer
+    assert log[-1] == ("sync", "a")
+    _ = a.array_ro
+    assert log.count(("sync", "a")) == 1
+    with pytest.raises(ValueError):
+        a.array_ro[0] = 7.0
+    # the device changes both vectors to the same content (fused step): b is a's twin
+    dev["a"] = dev["b"] = np.array([9.0, 8.0, 7.0, 6.0])
+    a.mark_device_newer()
+    b.mark_device_newer(twin_of=a)
+    log.clear()
+    assert a.array_ro.tolist() == [9, 8, 7, 6] and log == [("down", "a")]
+    assert b.array_ro.tolist() == [9, 8, 7, 6] and log == [("down", "a")]   # copied on the host, no second transfer
+    # ... but not when the twin moved on in between
+    dev["a"], dev["b"] = np.full(4, 1.0), np.full(4, 2.0)
+    a.mark_device_newer()
+    b.mark_device_newer(twin_of=a)
+    a.mark_device_newer()                                # a changed again: b must fetch its own content
+    log.clear()
+    assert b.array_ro.tolist() == [2, 2, 2, 2] and log == [("down", "b")]

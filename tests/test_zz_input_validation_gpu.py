@@ -92,3 +92,36 @@ def test_stencil_dictionary_is_bit_identical(ctx_factory, monkeypatch, x0):
     assert out["sell"][4] > 0 and out["sell"][2] > 3
     for a, b in zip(out["sell"][:6], out["dict"][:6]):
         assert np.array_equal(np.asarray(a), np.asarray(b))
+
+
+@pytest.mark.parametrize("ksp", [0, 1])
+def test_storage_modes_agree(ctx_factory, monkeypatch, ksp):
+    """The same solve in every storage mode of the persistent kernel - A rows and vectors in shared memory (default on
+    this small mesh), vectors only (MONO_PDE_NO_MATSMEM), streaming with TMA-staged slices (MONO_PDE_STREAM), streaming
+    with direct loads (+ MONO_PDE_NO_STAGING): same iteration count, iterates equal to rounding."""
+    from beat_b200 import fem
+
+    mesh = fem.create_box(fem.COMM_SELF, [np.zeros(3), np.array([20.0, 7.0, 3.0])], [40, 14, 6])
+    indptr, indices, mass, stiff = fem.assemble_p1_local(mesh, np.diag([0.1334, 0.0176, 0.0176]))
+    n = indptr.size - 1
+    v_prev = -85.0 + 120.0 * np.random.default_rng(3).random(n)
+    results = {}
+    for label, env in (("matsmem", {}), ("resident", {"MONO_PDE_NO_MATSMEM": "1"}), ("staged", {"MONO_PDE_STREAM": "1"}),
+                       ("direct", {"MONO_PDE_STREAM": "1", "MONO_PDE_NO_STAGING": "1"})):
+        for k in ("MONO_PDE_NO_MATSMEM", "MONO_PDE_STREAM", "MONO_PDE_NO_STAGING", "MONO_PDE_DICT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = ctx_factory()
+        ctx.pde_set_matrices(n, 0, indptr, indices, mass, stiff)
+        ctx.pde_config(1.0, 0.5, 1e-10, 1e-50, 200, 1, 0, 0)
+        ctx.pde_set_ksp_type(ksp)
+        ctx.set_v_prev(v_prev)
+        ctx.pde_step(0.0, 0.05)
+        results[label] = (ctx.get_v(np.empty(n)), ctx.ksp_info())
+        ctx.close()
+    x0, (its0, _, reason0) = results["matsmem"]
+    assert reason0 > 0 and its0 > 3
+    for label, (x, (its, _, reason)) in results.items():
+        assert (its, reason) == (its0, reason0), label
+        assert np.abs(x - x0).max() <= 1e-12 * np.abs(x0).max(), label

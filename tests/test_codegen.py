@@ -60,3 +60,135 @@ def test_rush_larsen_uses_the_total_derivative():
 @needs_reference
 def test_committed_generated_files_are_current():
     assert generate.main(["--check", "--odes", ODES]) == 0
+
+
+def _eval_node(x, env, memo=None):
+    """Scalar evaluation of one IR node (the same operations tests/_ir_eval.py interprets, on Python floats)."""
+    import math
+
+    memo = {} if memo is None else memo
+    r = memo.get(id(x))
+    if r is not None:
+        return r
+    k, a = x.kind, x.args
+    ev = lambda n: _eval_node(n, env, memo)  # noqa: E731
+    if k == "num":
+        r = x.value
+    elif k == "sym":
+        v = env[x.value]
+        r = ev(v) if hasattr(v, "kind") else v
+    elif k == "add":
+        r = ev(a[0]) + ev(a[1])
+    elif k == "sub":
+        r = ev(a[0]) - ev(a[1])
+    elif k == "mul":
+        r = ev(a[0]) * ev(a[1])
+    elif k == "div":
+        r = ev(a[0]) / ev(a[1])
+    elif k == "neg":
+        r = -ev(a[0])
+    elif k == "pow":
+        r = ev(a[0]) ** ev(a[1])
+    elif k == "call":
+        r = {"exp": math.exp, "log": math.log, "sqrt": math.sqrt, "floor": math.floor, "abs": abs}[x.value](ev(a[0]))
+    elif k == "cond":
+        r = ev(a[1]) if ev(a[0]) else ev(a[2])
+    elif k in ("lt", "gt", "le", "ge"):
+        p, q = ev(a[0]), ev(a[1])
+        r = {"lt": p < q, "gt": p > q, "le": p <= q, "ge": p >= q}[k]
+    else:
+        raise NotImplementedError(k)
+    memo[id(x)] = r
+    return r
+
+
+def test_differentiation_against_finite_differences_on_random_expressions():
+    """ir.diff - product / both quotient forms / power / exp / log / sqrt / abs / Conditional, and the chain-rule hook
+    through named intermediates that the total-derivative Rush-Larsen step relies on - against a 4th-order central
+    difference on 300 random expression DAGs."""
+    import random
+
+    from codegen import ir
+
+    rnd = random.Random(7)
+    y, p, u = ir.sym("y"), ir.sym("p"), ir.sym("u")  # state, parameter, named intermediate u = u(y)
+    u_def = ir.call("exp", ir.mul(ir.num(0.3), y)) + ir.mul(p, y)
+
+    def leaf():
+        return rnd.choice([y, y, p, u, ir.num(rnd.choice([0.5, 1.0, 2.0, -1.5, 3.0]))])
+
+    def positive(e):  # keep log / sqrt / non-integer powers in their domain
+        return ir.add(ir.mul(e, e), ir.num(0.7))
+
+    def tree(depth):
+        if depth == 0:
+            return leaf()
+        a, b = tree(depth - 1), tree(depth - 1)
+        op = rnd.randrange(11)
+        if op == 0:
+            return ir.add(a, b)
+        if op == 1:
+            return ir.sub(a, b)
+        if op == 2:
+            return ir.mul(a, b)
+        if op == 3:
+            return ir.div(a, positive(b))
+        if op == 4:
+            return ir.div(ir.num(rnd.choice([1.0, -2.0, 0.25])), positive(b))  # constant numerator: the division-free rule
+        if op == 5:
+            return ir.call("exp", ir.mul(ir.num(0.2), a))
+        if op == 6:
+            return ir.call("log", positive(a))
+        if op == 7:
+            return ir.call("sqrt", positive(a))
+        if op == 8:
+            return ir.power(positive(a), ir.num(rnd.choice([2.0, 3.0, 1.4, 0.24])))
+        if op == 9:
+            return ir.call("abs", ir.sub(a, ir.num(0.123)))
+        return ir.cond(ir.cmp("lt", a, ir.num(0.4)), b, ir.neg(a))
+
+    du = ir.diff(u_def, "y")
+    checked = 0
+    for _ in range(300):
+        e = tree(rnd.randint(1, 4))
+        de = ir.diff(e, "y", sym_diff=lambda name: du if name == "u" else ir.ZERO)
+        y0, p0, h = rnd.uniform(-1.2, 1.2), rnd.uniform(0.3, 1.5), 1e-3
+
+        def f(yv):
+            return _eval_node(e, {"y": yv, "p": p0, "u": u_def})
+
+        try:
+            vals = [f(y0 + k * h) for k in (-2, -1, 1, 2)]
+            got = _eval_node(de, {"y": y0, "p": p0, "u": u_def})
+        except (OverflowError, ZeroDivisionError, ValueError):
+            continue
+        fd = (vals[0] - 8 * vals[1] + 8 * vals[2] - vals[3]) / (12 * h)
+        # skip points where a Conditional / abs switches branch inside the stencil (the derivative jumps there)
+        branches = {repr(_branch_signature(e, {"y": y0 + k * h, "p": p0, "u": u_def})) for k in (-2, -1, 0, 1, 2)}
+        if len(branches) > 1 or not all(map(lambda v: abs(v) < 1e6, vals + [got])):
+            continue
+        assert abs(got - fd) <= 1e-6 * max(1.0, abs(fd), *map(abs, vals)), (e, got, fd)
+        checked += 1
+    assert checked >= 200
+
+
+def _branch_signature(x, env, memo=None, out=None):
+    """Which way every Conditional / abs of the expression goes at this point."""
+    out = [] if out is None else out
+    seen = set() if memo is None else memo
+
+    def walk(n):
+        if id(n) in seen:
+            return
+        seen.add(id(n))
+        if n.kind == "sym" and hasattr(env.get(n.value), "kind"):
+            walk(env[n.value])
+        if n.kind == "cond":
+            out.append(bool(_eval_node(n.args[0], env)))
+        if n.kind == "call" and n.value == "abs":
+            out.append(_eval_node(n.args[0], env) >= 0)
+        for a in n.args:
+            walk(a)
+
+    walk(x)
+    return out

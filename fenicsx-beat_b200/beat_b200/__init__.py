@@ -8,7 +8,7 @@ stimulation.  ``beat_b200.fem`` stands in for the few dolfinx/ufl objects those 
 ``beat_b200.models`` holds the compiled cell models (device handles with a gotranx-module-like surface).
 """
 
-from . import conductivities, fem, geometry, models, monodomain_model, monodomain_solver, odesolver, single_cell, stimulation, telemetry
+from . import conductivities, fem, geometry, models, monodomain_model, monodomain_solver, odesolver, single_cell, stimulation, telemetry, units
 from .monodomain_model import MonodomainModel
 from .monodomain_solver import MonodomainSplittingSolver
 from .stimulation import Stimulus
@@ -19,6 +19,6 @@ monodomain_model.Stimulus = Stimulus
 
 __all__ = [
     "MonodomainModel", "MonodomainSplittingSolver", "Stimulus", "BaseMonitor", "NullMonitor", "PerformanceMonitor",
-    "odesolver", "single_cell", "conductivities", "geometry", "stimulation", "telemetry", "fem", "models", "base_model",
+    "odesolver", "single_cell", "conductivities", "geometry", "stimulation", "telemetry", "units", "fem", "models", "base_model",
 ]
 __version__ = "0.1.0"

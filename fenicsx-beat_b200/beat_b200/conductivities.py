@@ -9,16 +9,17 @@ from typing import NamedTuple
 import numpy as np
 
 from .fem import Constant
+from .units import PerLength
 
 
 def default_conductivities(name: str = "Niederer") -> dict[str, float]:
-    """g_* in S/m, chi in 1/cm (the reference returns pint quantities in these units)."""
+    """g_* in S/m (plain floats), chi as ``PerLength(.., "cm")`` (the reference returns pint quantities in these units)."""
     if name == "Niederer":
-        return {"g_il": 0.17, "g_it": 0.019, "g_el": 0.62, "g_et": 0.24, "chi": 1400.0}
+        return {"g_il": 0.17, "g_it": 0.019, "g_el": 0.62, "g_et": 0.24, "chi": PerLength(1400.0, "cm")}
     if name == "Bishop":
-        return {"g_il": 0.34, "g_it": 0.060, "g_el": 0.12, "g_et": 0.08, "chi": 1400.0}
+        return {"g_il": 0.34, "g_it": 0.060, "g_el": 0.12, "g_et": 0.08, "chi": PerLength(1400.0, "cm")}
     if name == "Potse":  # mS/cm -> S/m is a factor 0.1
-        return {"g_il": 0.3, "g_it": 0.03, "g_el": 0.3, "g_et": 0.12, "chi": 800.0}
+        return {"g_il": 0.3, "g_it": 0.03, "g_el": 0.3, "g_et": 0.12, "chi": PerLength(800.0, "cm")}
     raise ValueError(f"Unknown conductivity tensor {name}")
 
 
@@ -29,8 +30,10 @@ class Conductivities(NamedTuple):
 
 def get_harmonic_mean_conductivity(chi: float, g_il: float = 0.17, g_it: float = 0.019, g_el: float = 0.62,
                                    g_et: float = 0.24) -> Conductivities:
-    """sigma = g_i g_e / (g_i + g_e) [S/m], scaled by 1/chi [chi in 1/cm] and expressed in uA/mV
-    (conductivities.py:63-98): S/m / (1/cm) = S/m * 0.01 m = 0.01 S = 10 uA/mV."""
+    """sigma = g_i g_e / (g_i + g_e) [S/m], scaled by 1/chi and expressed in uA/mV (conductivities.py:63-98):
+    S/m / (1/cm) = S/m * 0.01 m = 0.01 S = 10 uA/mV.  ``chi``: PerLength, or a plain number taken in 1/cm (the reference
+    cannot convert a unit-less chi here at all: pint raises)."""
+    chi = float(chi.to("cm")) if isinstance(chi, PerLength) else float(chi)
 
     def harmonic_mean(a, b):
         return a * b / (a + b)

@@ -219,6 +219,11 @@ class MonodomainModel:
                 self._ctx.stim_set_amplitude(self._stim_ids[k], amp)
                 self._stim_amp[k] = amp
 
+    def has_host_evaluated_sources(self) -> bool:
+        """True when some source amplitude is a function of time the HOST evaluates each step (TimeFunction / Separable):
+        such a source cannot be left alone on the device for several steps (MonodomainSplittingSolver.solve_on_device)."""
+        return any(isinstance(s.expr, fem.TimeFunction) for s in self._I_s)
+
     def _flush_host(self) -> None:
         self._state.x.flush_to_device()
         self.v_.x.flush_to_device()

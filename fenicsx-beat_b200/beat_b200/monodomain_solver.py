@@ -97,13 +97,28 @@ class MonodomainSplittingSolver:
 
     def solve_on_device(self, t0: float, dt: float, nsteps: int) -> None:
         """``nsteps`` fixed-dt steps without returning to Python between them (mono_split_solve): the
-        reference's ``solve`` loop for constant stimuli/windows, minus the per-step interpreter cost."""
+        reference's ``solve`` loop minus the per-step interpreter cost.  Only stimuli whose amplitude is constant over the
+        call can stay on the device for it (``TimeWindow``: the window test is part of the RHS kernel; plain constants).
+        A source whose amplitude the HOST evaluates every step (``fem.TimeFunction`` / ``fem.Separable`` h(t)) would be
+        frozen at its first value, so with any of those the call takes the per-step path - same result as ``solve``."""
         if not self._fused:
             raise RuntimeError("solve_on_device needs a device DolfinODESolver sharing the PDE's context")
+        if nsteps <= 0:
+            return
+        if self.pde.has_host_evaluated_sources():
+            t = t0
+            for _ in range(nsteps):
+                self.step((t, t + dt))
+                t = t + dt
+            return
         self._prepare_fused(t0, t0 + dt)
         self.pde._ctx.split_solve(t0, dt, nsteps, self.theta)
         self.pde.time.value = t0 + (nsteps - 1) * dt + self.pde.parameters["theta"] * dt
         self._mark_fused()
+        t = t0
+        for _ in range(nsteps):  # the monitors count steps as the reference's loop does (telemetry.py:86-92)
+            self.monitor.advance_step(t, t + dt)
+            t = t + dt
 
     def _step_protocol(self, interval):
         """Any other ODE backend (the 5-method ODESolver protocol): the hand-offs of the reference's step, one timed label

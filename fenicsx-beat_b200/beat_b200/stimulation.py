@@ -5,6 +5,7 @@ from __future__ import annotations
 from typing import NamedTuple
 
 from . import fem
+from .units import CM_PER_UNIT, PerLength
 
 
 class Stimulus(NamedTuple):
@@ -20,25 +21,56 @@ class Stimulus(NamedTuple):
         self.expr.amplitude = amp
 
 
-_TO_MESH_UNIT = {"m": 100.0, "dm": 10.0, "cm": 1.0, "mm": 0.1}  # 1 cm expressed in the mesh unit, inverted below
-
-
-def define_stimulus(mesh: fem.Mesh, chi: float, time: fem.Constant, subdomain_data: fem.MeshTags, marker: int,
-                    mesh_unit: str = "cm", duration: float = 2.0, amplitude: float = 500.0, start: float = 0.0) -> Stimulus:
-    """amplitude [uA/cm^effective_dim] / chi [1/cm] expressed in uA/mesh_unit^(effective_dim-1), active for
-    start <= time <= start + duration (stimulation.py:264-272; unit rules :27-207).
-
-    effective dimension: subdomain dimension seen as a slice of 3-D (stimulation.py:27-58)."""
-    if mesh_unit not in _TO_MESH_UNIT:
-        raise ValueError(f"Invalid mesh unit {mesh_unit}")
+def compute_effective_dim(mesh: fem.Mesh, subdomain_data: fem.MeshTags) -> int:
+    """Dimension used for the unit of the stimulus: subdomains of surfaces and lines are seen as slices of 3-D
+    (stimulation.py:27-58)."""
     tdim = mesh.topology.dim
-    effective_dim = subdomain_data.dim + (3 - tdim)
+    if tdim not in (1, 2, 3):
+        raise ValueError("Invalid mesh topology dimension")
+    return subdomain_data.dim + (3 - tdim)
+
+
+def get_dZ(mesh: fem.Mesh, subdomain_data: fem.MeshTags) -> fem.Measure:
+    """``ds`` for facet tags, ``dx`` for cell tags (stimulation.py:61-108)."""
+    tdim = mesh.topology.dim
+    if subdomain_data.dim == tdim - 1:
+        if tdim <= 1:
+            raise ValueError("Invalid mesh topology dimension")
+        return fem.Measure("ds", domain=mesh, subdomain_data=subdomain_data)
+    if subdomain_data.dim == tdim:
+        return fem.Measure("dx", domain=mesh, subdomain_data=subdomain_data)
+    raise ValueError("Invalid subdomain data dimension")
+
+
+def convert_chi(chi, mesh_unit: str) -> PerLength:
+    """A plain number is taken in 1/mesh_unit (the reference's rule, stimulation.py:186-207); a PerLength keeps its unit."""
+    if mesh_unit not in CM_PER_UNIT:
+        raise ValueError(f"Invalid mesh unit {mesh_unit}")
+    return chi if isinstance(chi, PerLength) else PerLength(float(chi), mesh_unit)
+
+
+def amplitude_exponent(effective_dim: int) -> int:
+    """A plain amplitude is in uA/cm^k with k = 1, 1, 2, 3 for effective dimension 0, 1, 2, 3 (stimulation.py:111-148)."""
     if effective_dim < 0 or effective_dim > 3:
-        raise ValueError("Invalid effective dimension")
-    cm_per_unit = _TO_MESH_UNIT[mesh_unit]  # length of one mesh unit in cm
-    # A/chi has unit uA/cm^(effective_dim-1); 1/cm^(k) = cm_per_unit^k / mesh_unit^k
-    amp = amplitude / chi * cm_per_unit ** (effective_dim - 1)
-    kind = "dx" if subdomain_data.dim == tdim else "ds"
-    dZ = fem.Measure(kind, domain=mesh, subdomain_data=subdomain_data)
+        raise ValueError(f"Invalid effective dimension {effective_dim}. Must be 0, 1, 2 or 3.")
+    return max(effective_dim, 1)
+
+
+def define_stimulus(mesh: fem.Mesh, chi, time: fem.Constant, subdomain_data: fem.MeshTags, marker: int,
+                    mesh_unit: str = "cm", duration: float = 2.0, amplitude: float = 500.0, start: float = 0.0) -> Stimulus:
+    """amplitude [uA/cm^k] / chi expressed in uA/mesh_unit^(effective_dim-1), active for start <= time <= start + duration
+    (stimulation.py:210-272 with the unit rules of :27-207 written out).
+
+    ``chi``: a plain number is in 1/mesh_unit, as in the reference; ``conductivities.default_conductivities`` hands out
+    ``PerLength(1400, "cm")`` like the reference's pint quantity, which is converted."""
+    if mesh_unit not in CM_PER_UNIT:
+        raise ValueError(f"Invalid mesh unit {mesh_unit}")
+    effective_dim = compute_effective_dim(mesh, subdomain_data)
+    k = amplitude_exponent(effective_dim)
+    u = CM_PER_UNIT[mesh_unit]  # length of one mesh unit in cm
+    chi_mesh = float(convert_chi(chi, mesh_unit).to(mesh_unit))  # 1/mesh_unit
+    # A/chi = (amplitude/chi_mesh) uA mesh_unit / cm^k, and 1/cm^k = u^k / mesh_unit^k
+    amp = amplitude / chi_mesh * u**k
+    dZ = get_dZ(mesh, subdomain_data)
     expr = fem.TimeWindow(time, start, start + duration, amp)
     return Stimulus(dZ=dZ, marker=marker, expr=expr)

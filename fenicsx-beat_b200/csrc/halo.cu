@@ -21,8 +21,10 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "mono_ctx.h"
 
@@ -33,6 +35,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
@@ -71,6 +74,7 @@ bool nccl_load() {
   g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
   g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
   g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+  g_nccl.CommAbort = reinterpret_cast<decltype(g_nccl.CommAbort)>(sym("ncclCommAbort"));
   g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
   g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(sym("ncclGroupStart"));
   g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
@@ -107,15 +111,51 @@ struct PeerMeta {
 
 }  // namespace
 
+// A barrier over the ranks on the context's stream (a 4-byte all-reduce), bounded in time: a peer that died must not
+// hang the teardown of the survivors.  Returns false when it timed out or could not be issued.
+static bool comm_barrier(mono_ctx* c, double timeout_s) {
+  if (!c->comm || c->nranks <= 1) return true;
+  int* d = nullptr;
+  if (cudaMalloc(&d, sizeof(int)) != cudaSuccess) return false;
+  cudaMemsetAsync(d, 0, sizeof(int), c->stream);
+  bool ok = g_nccl.AllReduce(d, d, 1, ncclInt, ncclSum, (ncclComm_t)c->comm, c->stream) == ncclSuccess;
+  if (ok) {
+    const auto t0 = std::chrono::steady_clock::now();
+    while (cudaStreamQuery(c->stream) == cudaErrorNotReady) {
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) {
+        ok = false;
+        break;
+      }
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    (void)cudaGetLastError();
+  }
+  if (ok) cudaFree(d);  // (a timed-out collective still owns the buffer: leak 4 bytes rather than free under it)
+  return ok;
+}
+
+// Collective teardown of the peer mappings: every rank's exchange allocation is mapped by its peers, whose persistent
+// kernels store into it.  Order: (1) my own work is done (caller synchronised the stream), (2) barrier: nobody launches
+// another store into my buffers, (3) close my mappings of the peers, (4) barrier: nobody still maps my allocation,
+// and only then does the caller free it.  With a dead peer the barriers time out and the teardown proceeds.
 int halo_destroy(mono_ctx* c) {
+  const bool collective = c->peers_ready && c->comm != nullptr && c->nranks > 1;
+  double tmo = 10.0;
+  if (const char* e = getenv("MONO_TEARDOWN_TIMEOUT_S")) tmo = std::max(0.0, atof(e));
+  bool alive = collective && tmo > 0.0 && comm_barrier(c, tmo);
   for (int q = 0; q < kMaxRanks; ++q) {
     if (c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
     c->peer_base[q] = nullptr;
     c->peer_xrecs[q] = nullptr;
   }
   c->peers_ready = false;
+  if (alive) alive = comm_barrier(c, tmo);
   if (c->comm) {
-    g_nccl.CommDestroy((ncclComm_t)c->comm);
+    // a communicator with a collective that never completed (dead peer) must be aborted: destroying it would wait
+    if (collective && !alive && tmo > 0.0)
+      g_nccl.CommAbort((ncclComm_t)c->comm);
+    else
+      g_nccl.CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
   }
   return MONO_OK;

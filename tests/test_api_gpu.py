@@ -326,6 +326,29 @@ def test_monodomain_splitting_analytic():
     assert _l2_error_vs_exact(solver, mesh, 50) < 0.002
 
 
+def test_solve_on_device_with_host_evaluated_source_equals_solve():
+    """A source whose amplitude the host evaluates each step (fem.Separable h(t)) must not be frozen at its first value by
+    solve_on_device (it falls back to the per-step loop); and the monitors count every step (telemetry.py:86-92)."""
+    beat = _beat()
+    a, mesh = _simple_split_solver(12)
+    b, _ = _simple_split_solver(12)
+
+    class Counter(beat.NullMonitor):
+        n = 0
+
+        def advance_step(self, t0, t1):
+            self.n += 1
+
+    b.monitor = Counter()
+    assert a.pde.has_host_evaluated_sources()
+    a.solve((0.0, 0.3), dt=0.01)
+    b.solve_on_device(0.0, 0.01, 30)
+    assert b.monitor.n == 30
+    assert np.array_equal(a.pde.state.x.array_ro, b.pde.state.x.array_ro)
+    assert np.array_equal(a.ode.values, b.ode.values)
+    assert float(a.pde.time.value) == float(b.pde.time.value)
+
+
 def test_monodomain_splitting_spatial_convergence():
     """tests/test_monodomain_solver.py:98-149: dt = 1e-3, T = 1, N = 8, 16, 32 -> mean rate > 1.85."""
     errors = []

@@ -77,8 +77,22 @@ def test_define_stimulus_units_and_window():  # tests/test_stimulation.py:253-30
     assert np.isclose(total(start + duration / 2), amplitude / chi)
     assert np.isclose(total(start + duration + 1e-6), 0.0)
     # mm mesh: uA/cm^2 -> uA/mm^2 for a cell stimulus in 2-D (effective dimension 3): factor 1e-2 (niederer_benchmark.py)
-    mm = stimulation.define_stimulus(mesh=mesh, chi=1400.0, time=time, amplitude=50000.0, mesh_unit="mm", marker=1, subdomain_data=tags)
+    from beat_b200.units import PerLength
+
+    chi_cm = conductivities.default_conductivities("Niederer")["chi"]
+    assert isinstance(chi_cm, PerLength) and chi_cm.unit == "cm" and float(chi_cm) == 1400.0 and float(chi_cm.to("mm")) == 140.0
+    mm = stimulation.define_stimulus(mesh=mesh, chi=chi_cm, time=time, amplitude=50000.0, mesh_unit="mm", marker=1, subdomain_data=tags)
     assert np.isclose(mm.expr.amplitude_now(), 50000.0 / 1400.0 * 1e-2)
+    # a plain number is 1/mesh_unit (src/beat/stimulation.py:186-207): (A uA/cm^3) / (chi /mm) -> uA/mm^2 = A/chi * 0.1^3
+    mmf = stimulation.define_stimulus(mesh=mesh, chi=140.0, time=time, amplitude=50000.0, mesh_unit="mm", marker=1, subdomain_data=tags)
+    assert np.isclose(mmf.expr.amplitude_now(), 50000.0 / 140.0 * 1e-3) and np.isclose(mmf.expr.amplitude_now(), mm.expr.amplitude_now())
+    mf = stimulation.define_stimulus(mesh=mesh, chi=1.4e5, time=time, amplitude=50000.0, mesh_unit="m", marker=1, subdomain_data=tags)
+    assert np.isclose(mf.expr.amplitude_now(), 50000.0 / 1.4e5 * 1e6)  # uA/m^2
+    # facet (ds) stimulus in 2-D: effective dimension 2, uA/cm^2 / chi -> uA/mesh_unit
+    facets = fem.locate_entities_boundary(mesh, 1, lambda x: np.isclose(x[0], 0.0))
+    ftags = fem.meshtags(mesh, 1, facets, np.full(len(facets), 2, dtype=np.int32))
+    fs = stimulation.define_stimulus(mesh=mesh, chi=chi_cm, time=time, amplitude=2000.0, mesh_unit="mm", marker=2, subdomain_data=ftags)
+    assert fs.dZ.kind == "ds" and np.isclose(fs.expr.amplitude_now(), 2000.0 / 1400.0 * 0.1)
     with pytest.raises(ValueError):
         stimulation.define_stimulus(mesh=mesh, chi=1.0, time=time, mesh_unit="inch", marker=1, subdomain_data=tags)
     stim.assign(7.0)  # Stimulus.assign, stimulation.py:23-24

@@ -57,7 +57,7 @@ def test_stimulus_and_probe_indices_are_validated(ctx_factory):
 
 @pytest.mark.parametrize("x0", [0, 1])
 def test_stencil_dictionary_is_bit_identical(ctx_factory, monkeypatch, x0):
-    """EXPERIMENTAL path (MONO_PDE_DICT=1): dictionary rows take their matrix entries from shared memory; same entries,
+    """Stencil dictionary (default; MONO_PDE_DICT=0 disables): dictionary rows take their matrix entries from shared memory; same entries,
     same order, so the solve must reproduce the SELL-streaming kernel bit for bit (iterate, iteration count, norm)."""
     from beat_b200 import fem
 
@@ -71,9 +71,9 @@ def test_stencil_dictionary_is_bit_identical(ctx_factory, monkeypatch, x0):
     out = {}
     for label in ("sell", "dict"):
         if label == "dict":
-            monkeypatch.setenv("MONO_PDE_DICT", "1")
+            monkeypatch.delenv("MONO_PDE_DICT", raising=False)  # the default
         else:
-            monkeypatch.delenv("MONO_PDE_DICT", raising=False)
+            monkeypatch.setenv("MONO_PDE_DICT", "0")
         ctx = ctx_factory()
         ctx.pde_set_matrices(n, 0, indptr, indices, mass, stiff)
         ctx.pde_config(1.0, 0.5, 1e-10, 1e-50, 200, 1, 0, x0)
@@ -110,6 +110,7 @@ def test_storage_modes_agree(ctx_factory, monkeypatch, ksp):
                        ("direct", {"MONO_PDE_STREAM": "1", "MONO_PDE_NO_STAGING": "1"})):
         for k in ("MONO_PDE_NO_MATSMEM", "MONO_PDE_STREAM", "MONO_PDE_NO_STAGING", "MONO_PDE_DICT"):
             monkeypatch.delenv(k, raising=False)
+        monkeypatch.setenv("MONO_PDE_DICT", "0")  # (the dictionary has its own bit-identity test above)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ctx = ctx_factory()

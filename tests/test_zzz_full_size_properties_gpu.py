@@ -90,12 +90,12 @@ def test_cell_model_kernel_is_pointwise_at_full_size(ctx_factory, tag, n_nodes):
 
 
 def test_stencil_dictionary_at_3p4M_dofs_is_bit_identical(ctx_factory, slab_005, monkeypatch):
-    """The experimental dictionary kernel (MONO_PDE_DICT=1) against the SELL kernel at full size: many slices per warp,
+    """The dictionary kernel (default) against the SELL kernel (MONO_PDE_DICT=0) at full size: many slices per warp,
     two steps with a dt change in between."""
     steps = ((0.0, 0.01), (0.01, 0.03))
-    monkeypatch.delenv("MONO_PDE_DICT", raising=False)
+    monkeypatch.setenv("MONO_PDE_DICT", "0")
     ref, info0, _ = _solve(ctx_factory, slab_005, 0, 0, steps)
-    monkeypatch.setenv("MONO_PDE_DICT", "1")
+    monkeypatch.delenv("MONO_PDE_DICT", raising=False)
     got, info1, _ = _solve(ctx_factory, slab_005, 0, 0, steps)
     assert not info0["active"] and info1["active"] and info1["patterns"] == 27 and info1["rows_covered"] == 1.0
     for (xa, ka), (xb, kb) in zip(ref, got):

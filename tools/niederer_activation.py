@@ -42,7 +42,7 @@ def main(argv=None) -> int:
     ap.add_argument("--ksp", default="auto", choices=["auto", "cg", "pipecg"])
     ap.add_argument("--rtol", type=float, default=None, help="default: PETSc's 1e-5, as the demo runs it")
     ap.add_argument("--chunk", type=int, default=500, help="steps per mono_split_solve call (progress / early stop granularity)")
-    ap.add_argument("--matrix-dict", action="store_true", help="EXPERIMENTAL stencil dictionary (MONO_PDE_DICT=1)")
+    ap.add_argument("--no-matrix-dict", action="store_true", help="disable the stencil dictionary (MONO_PDE_DICT=0)")
     args = ap.parse_args(argv)
 
     import numpy as np
@@ -59,8 +59,8 @@ def main(argv=None) -> int:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.matrix_dict:
-        os.environ["MONO_PDE_DICT"] = "1"
+    if args.no_matrix_dict:
+        os.environ["MONO_PDE_DICT"] = "0"
     t_setup = time.perf_counter()
     solver, info = niederer.setup(dx=args.dx, comm=fem.Comm(rank, world), rtol=args.rtol, ksp_type=args.ksp, probes=True)
     ctx = solver.pde._ctx
@@ -109,7 +109,7 @@ def main(argv=None) -> int:
             "max_abs_diff_to_published_ms": float(np.abs(act - np.array(pub)).max()) if pub else None,
             "steps": done, "run_s": run_s, "setup_s": setup_s, "node_steps_per_s": info["n_global"] * done / run_s,
             "cg_iterations_per_step": its / max(solves, 1), "ksp": solver.pde.ksp_type_used, "pc": solver.pde.pc_type_used,
-            "matrix_dictionary": ctx.pde_dictionary_info() if args.matrix_dict else None,
+            "matrix_dictionary": ctx.pde_dictionary_info(),
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -520,7 +520,7 @@ def measure(D: Dist, args, workload: str, scaling: str, K: int, W: int, full: bo
     barrier()
     del solver, ode, pde
     ctx.close()
-    barrier()
+    D.barrier()
     return rec
 
 

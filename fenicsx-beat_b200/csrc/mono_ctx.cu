@@ -167,7 +167,7 @@ int mono_ctx_destroy(mono_ctx* c) {
                   (void*)c->v_prev, (void*)c->work[0], (void*)c->work[1], (void*)c->work[2], (void*)c->work[3],
                   (void*)c->work[4], (void*)c->work[5], (void*)c->work[6], (void*)c->work[7], (void*)c->work[8], (void*)c->work[9],
                   (void*)c->stim_vec,
-                  (void*)c->gen_state, (void*)c->send_of_row_dev, (void*)c->send_ents_dev, (void*)c->region_table, (void*)c->region_of_node,
+                  (void*)c->gen_state, (void*)c->send_of_row_dev, (void*)c->send_ents_dev, (void*)c->slice_send_dev, (void*)c->region_table, (void*)c->region_of_node,
                   (void*)c->recs, (void*)c->timeline_dev,
                   (void*)c->ksp_dev, (void*)c->probes_dev,
                   (void*)c->probe_vals_dev, (void*)c->probe_act_dev, (void*)c->flush_buf, (void*)c->send_idx_dev,

@@ -103,6 +103,7 @@ struct mono_ctx {
   SyncRec* peer_xrecs[kMaxRanks] = {};
   int32_t* send_of_row_dev = nullptr;      // n_owned: first send entry of a row, -1 for interior rows
   void* send_ents_dev = nullptr;           // SendEnt[n_send] (pde_kernels.cu)
+  uint8_t* slice_send_dev = nullptr;       // n_slices: 1 when a row of the slice has a send list
   int ksp_type = MONO_KSP_CG;
   double C_m = 1.0, theta = 0.5, rtol = 1e-5, atol = 1e-50;
   int max_it = 10000, pc_type = MONO_PC_JACOBI, norm_type = MONO_NORM_PRECONDITIONED, x0_mode = MONO_X0_ZERO;
@@ -121,8 +122,9 @@ struct mono_ctx {
   bool matsmem = false;             // ... and so do the A entries (one row per thread)
   bool resident = false;            // the CG vectors of a CTA's rows fit in shared memory
   bool staged = false;              // streaming mode: SELL slices reach the SpMV through TMA-staged shared memory
+  bool stream_plain = false;        // streaming KSPCG runs pde_cg_stream_kernel (plain vectors + fenced barrier)
   size_t resident_smem = 0;
-  // stencil dictionary of the matrices (EXPERIMENTAL, MONO_PDE_DICT=1; pde_build_sell): rows whose (column offsets, values)
+  // stencil dictionary of the matrices (default, MONO_PDE_DICT=0 disables; pde_build_sell): rows whose (column offsets, values)
   // repeat take their entries from a small table in shared memory instead of the SELL stream
   int n_pat = 0;                    // patterns in the dictionary (0: none)
   double dict_cover = 0.0;          // fraction of the owned rows the dictionary covers

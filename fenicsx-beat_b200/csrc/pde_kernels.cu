@@ -94,6 +94,7 @@ struct PdeArgs {
   SyncRec* peer_xrecs[kMaxRanks];   // every rank's cross-rank reduction records [2 parities][4 slots][nranks]
   const int32_t* send_of_row;       // owned row -> first entry of its send list (-1: interior row)
   const SendEnt* send_ents;
+  const uint8_t* slice_send;        // per SELL slice: 1 when some row of it has a send list (streaming kernel: skips the lookups)
   KspResult* res;
   u64* timeline;                    // optional (measurement): globaltimer stamps of CTA 0 at phase boundaries
   // ---- stencil dictionary (DICT kernels only) ----
@@ -155,6 +156,13 @@ __device__ __forceinline__ void ld_tag(const SyncRec* p, double& v, u64& g) {
   v = __longlong_as_double(a);
 }
 
+// ordinary (L1-allocating) load of data that other CTAs wrote during this launch and a fenced barrier made visible
+__device__ __forceinline__ double ld_coherent(const double* p) {
+  double v;
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ u64 global_ns() {
   u64 t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -196,7 +204,10 @@ __device__ __forceinline__ double wait_tag(const SyncRec* p, u64 want, int* fail
 __device__ __forceinline__ SyncRec* partial_recs(const PdeArgs& a, u64 gen) { return a.recs + (size_t)(gen & 1ull) * 4 * a.n_workers; }
 __device__ __forceinline__ SyncRec* total_recs(const PdeArgs& a, u64 gen) { return a.recs + (size_t)8 * a.n_workers + (gen & 1ull) * 4; }
 
-template <int NV>
+// FENCE (streaming kernel): the reduction doubles as a grid barrier with memory ordering - everything the CTAs wrote with
+// plain stores before post() is visible to plain loads issued after wait() (the cooperative-groups grid.sync pattern:
+// bar.sync ; fence ; flag store ... flag load ; fence ; bar.sync - the fence of the polling thread also invalidates the L1).
+template <int NV, bool FENCE = false>
 __device__ __forceinline__ void post(const double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -211,7 +222,10 @@ __device__ __forceinline__ void post(const double (&v)[NV], const PdeArgs& a, u6
     for (int k = 0; k < NV; ++k) {
       double s = lane < kWarpsPerBlock ? sh.warp_part[k * kWarpsPerBlock + lane] : 0.0;
       s = warp_sum(s);
-      if (lane == 0) st_tag(part + (size_t)k * a.n_workers + blockIdx.x, s, gen);
+      if (lane == 0) {
+        if constexpr (FENCE) __threadfence();
+        st_tag(part + (size_t)k * a.n_workers + blockIdx.x, s, gen);
+      }
     }
   }
 }
@@ -224,21 +238,27 @@ __device__ __forceinline__ void post(const double (&v)[NV], const PdeArgs& a, u6
 // memory + mbarriers, leaders all-to-all through tagged global records, totals written back into the members' shared
 // memory - micro-benchmarked at 2.87 us per reduction (8-CTA clusters, 15 leaders) against 2.14 us for this
 // reducer-CTA scheme: the two DSMEM hand-offs are not cheaper than the L2 hop they replace, and the chain is longer.)
-template <int NV>
+template <int NV, bool FENCE = false>
 __device__ __forceinline__ void wait(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
-  if (threadIdx.x < NV) sh.totals[threadIdx.x] = wait_tag(total_recs(a, gen) + threadIdx.x, gen, &sh.fail, a.spin_ns);
+  if (threadIdx.x < NV) {
+    sh.totals[threadIdx.x] = wait_tag(total_recs(a, gen) + threadIdx.x, gen, &sh.fail, a.spin_ns);
+    if constexpr (FENCE) __threadfence();
+  }
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NV; ++k) v[k] = sh.totals[k];
   __syncthreads();
 }
 
-template <int NV, bool MULTI>
+template <int NV, bool MULTI, bool FENCE = false>
 __device__ __forceinline__ void reduce_publish(double (&v)[NV], const PdeArgs& a, u64 gen, Scratch& sh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned nw = a.n_workers;
   const SyncRec* part = partial_recs(a, gen);
-  for (unsigned idx = threadIdx.x; idx < NV * nw; idx += kPdeThreads) sh.red[idx] = wait_tag(part + idx, gen, &sh.fail, a.spin_ns);
+  for (unsigned idx = threadIdx.x; idx < NV * nw; idx += kPdeThreads) {
+    sh.red[idx] = wait_tag(part + idx, gen, &sh.fail, a.spin_ns);
+    if constexpr (FENCE) __threadfence();  // acquire side of every worker's release; the barrier below makes it cumulative
+  }
   __syncthreads();
   if (warp < NV) {
     double s = 0.0;
@@ -254,6 +274,7 @@ __device__ __forceinline__ void reduce_publish(double (&v)[NV], const PdeArgs& a
       for (int q = 0; q < a.nranks; ++q) s += __shfl_sync(0xffffffffu, mine, q);  // rank order: same bits everywhere
     }
     if (lane == 0) {
+      if constexpr (FENCE) __threadfence();
       st_tag(total_recs(a, gen) + warp, s, gen);
       sh.totals[warp] = s;
     }
@@ -425,7 +446,7 @@ struct Stager {
 // q_row = sum_k val_k * g(col_k) for the slice `s` of this warp: entries come from the stage buffers (moved to
 // registers at once so the buffer can be refilled), the gathered vector is tagged.
 template <bool TAGGED, bool SYS>
-__device__ __forceinline__ double staged_row(const PdeArgs& a, Stager& S, const double* vals, int64_t s, int64_t warp_stride, int lane,
+__device__ __forceinline__ double staged_row(const PdeArgs& a, Stager& S, const double* vals, int64_t s, int64_t s_prefetch, int lane,
                                              const void* vec, u64 want, int* fail) {
   const int64_t beg = __ldg(a.slice_ptr + s);
   const int width = (int)((__ldg(a.slice_ptr + s + 1) - beg) / kSlice);
@@ -441,7 +462,7 @@ __device__ __forceinline__ double staged_row(const PdeArgs& a, Stager& S, const 
     av[u] = u < width ? sA[u * kSlice + lane] : 0.0;
   }
   __syncwarp();
-  if (lane == 0 && s + 2 * warp_stride < a.n_slices) S.issue(a, vals, s + 2 * warp_stride, S.count + 2);
+  if (lane == 0 && s_prefetch >= 0) S.issue(a, vals, s_prefetch, S.count + 2);  // s_prefetch: the warp's slice after next, -1: none
   S.count++;
   if constexpr (TAGGED) {
     const SyncRec* tv = static_cast<const SyncRec*>(vec);
@@ -464,6 +485,51 @@ __device__ __forceinline__ double staged_row(const PdeArgs& a, Stager& S, const 
     const double* dv = static_cast<const double*>(vec);
 #pragma unroll
     for (int u = 0; u < kChunk; ++u) g[u] = c[u] >= 0 ? __ldg(dv + c[u]) : 0.0;
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) acc = fma(av[u], g[u], acc);
+  return acc;
+}
+
+// the same for the streaming kernel's plain search direction: owned columns with ordinary loads, ghost columns (MULTI)
+// from the tagged exchange buffer
+template <bool MULTI>
+__device__ __forceinline__ double staged_row_p(const PdeArgs& a, Stager& S, const double* vals, int64_t s, int64_t s_prefetch, int lane,
+                                               const double* p, const SyncRec* ghost_tb, u64 want, int* fail) {
+  const int64_t beg = __ldg(a.slice_ptr + s);
+  const int width = (int)((__ldg(a.slice_ptr + s + 1) - beg) / kSlice);
+  const unsigned st = S.count & 1u;
+  mbar_wait(S.bar[st], (S.count >> 1) & 1u);
+  const double* sA = reinterpret_cast<const double*>(S.base + st * kStageBytes);
+  const int32_t* sC = reinterpret_cast<const int32_t*>(S.base + st * kStageBytes + kStageValBytes);
+  int32_t c[kChunk];
+  double av[kChunk], g[kChunk];
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) {
+    c[u] = u < width ? sC[u * kSlice + lane] : -1;
+    av[u] = u < width ? sA[u * kSlice + lane] : 0.0;
+  }
+  __syncwarp();
+  if (lane == 0 && s_prefetch >= 0) S.issue(a, vals, s_prefetch, S.count + 2);
+  S.count++;
+  unsigned ghost = 0;
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) {
+    g[u] = 0.0;
+    if (c[u] >= 0) {
+      if (MULTI && c[u] >= a.n_owned)
+        ghost |= 1u << u;
+      else
+        g[u] = ld_coherent(p + c[u]);
+    }
+  }
+  if constexpr (MULTI) {
+    if (ghost) {
+#pragma unroll
+      for (int u = 0; u < kChunk; ++u)
+        if (ghost & (1u << u)) g[u] = wait_tag<true>(ghost_tb + c[u], want, fail, a.spin_ns);
+    }
   }
   double acc = 0.0;
 #pragma unroll
@@ -734,10 +800,12 @@ __device__ void pipecg_reducer(const PdeArgs& a, Scratch& sh, u64 gen) {
   finish_reducer(a, sh, gen, its, reason, rnorm);
 }
 
-template <bool MULTI>
+// BARRIER (streaming kernel): the first reduction and one more per iteration (after the new search direction was
+// written) are grid barriers with memory ordering, see post().
+template <bool MULTI, bool BARRIER = false>
 __device__ void cg_reducer(const PdeArgs& a, Scratch& sh, u64 gen) {
   double acc3[3];
-  reduce_publish<3, MULTI>(acc3, a, gen++, sh);
+  reduce_publish<3, MULTI, BARRIER>(acc3, a, gen++, sh);
   double rnorm = sqrt(fabs(acc3[1]));
   const double ttol = fmax(a.rtol * sqrt(fabs(acc3[2])), a.atol);
   int its = 0;
@@ -751,6 +819,12 @@ __device__ void cg_reducer(const PdeArgs& a, Scratch& sh, u64 gen) {
     rnorm = sqrt(fabs(acc2[1]));
     reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(pq[0] == pq[0]) || pq[0] == 0.0);
     if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+    if constexpr (BARRIER) {
+      if (reason == 0) {
+        double one[1];
+        reduce_publish<1, MULTI, true>(one, a, gen++, sh);
+      }
+    }
   }
   finish_reducer(a, sh, gen, its, reason, rnorm);
 }
@@ -905,7 +979,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
         r.slot = 0;
         const bool on = r.row < a.n_owned;
         const double sv = (on && a.has_stim) ? __ldg(a.stim_vec + r.row) : 0.0;
-        double bi = staged_row<false, false>(a, S, a.B, s, warp_stride, lane, a.v_prev, 0, &sh.fail);
+        double bi = staged_row<false, false>(a, S, a.B, s, s + 2 * warp_stride < a.n_slices ? s + 2 * warp_stride : -1, lane, a.v_prev, 0, &sh.fail);
         if (on) {
           if (a.has_stim) bi = fma(a.dt, sv, bi);
           rhs_finish(r, bi, 0.0);
@@ -960,7 +1034,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
         for (int64_t s = warp_global; s < a.n_slices; s += warp_stride) {
           const int64_t row = s * kSlice + lane;
           const double pi = row < a.n_owned ? __ldcg(a.work[VP] + row) : 0.0;  // requested before the gathers
-          const double qi = staged_row<true, MULTI>(a, S, a.A, s, warp_stride, lane, a.tb[cur], vtag, &sh.fail);
+          const double qi = staged_row<true, MULTI>(a, S, a.A, s, s + 2 * warp_stride < a.n_slices ? s + 2 * warp_stride : -1, lane, a.tb[cur], vtag, &sh.fail);
           if (row < a.n_owned) {
             __stcg(a.work[VQ] + row, qi);
             pq[0] = fma(pi, qi, pq[0]);
@@ -1036,6 +1110,350 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_kernel(const PdeArgs a)
     stamp(a, nstamp);
   }
   FINISH_SOLVE(gen)
+}
+
+// ---- KSPCG for meshes that stream from HBM: plain vectors, one memory-ordered grid barrier per iteration ------------
+// Same iterates as pde_cg_kernel.  What is different is how data crosses CTAs, because the trade-off flips with size:
+// a resident mesh is latency bound (a fenced barrier costs microseconds, so values travel with tags and nothing ever
+// waits for a barrier), a streamed mesh is bandwidth bound (a phase takes 50-500 us, a fenced barrier ~3 us), and there
+// the tagged exchange costs 16 B per element on every gather plus a second copy of the search direction.  So here
+//   * the search direction p is ONE plain fp64 vector; the reduction that follows its update is a grid barrier with
+//     release/acquire ordering (post/wait/reduce_publish with FENCE), after which the SpMV gathers it with ordinary
+//     L1-cached loads (the acquire fence of the polling thread invalidated the L1) - 8 B per gathered element, and the
+//     elements of neighbouring rows come out of the L1 instead of the L2;
+//   * only GHOST columns (multi-GPU) still use the tagged exchange buffers: peers store them straight into this rank's
+//     ghost slots and the gather polls the tag of exactly the ghost elements it needs, so no cross-GPU fence exists;
+//   * every CTA owns one contiguous run of SELL slices (warp w takes slices begin + w, + 16, ...): the y-neighbours of
+//     a row were gathered by the same SM a few trips earlier, so they hit its L1; 147 sequential streams keep the HBM
+//     pages open;
+//   * vector phases take four rows per thread and trip, dictionary SpMV rows two, so that a 512-thread CTA keeps
+//     ~80 KB of loads in flight (Little: 43 GB/s per SM x ~1 us).
+// Per iteration and row (dictionary rows): SpMV 8 (p, once per line through L1/L2) + 8 (q) + 1 (pattern), update
+// 40 + 16, direction 24 + 8 = 105 B against 137 B + 240 B of L2 gather traffic for the tagged kernel.
+// gather of the search direction for one SELL/dictionary entry list: owned columns from the plain vector, ghost columns
+// (MULTI) from the tagged exchange buffer the owner rank stores into
+template <bool MULTI, class ColF, class ValF>
+__device__ __forceinline__ double row_times_p(const PdeArgs& a, int width, ColF col, ValF val, const double* p, const SyncRec* ghost_tb,
+                                              u64 want, int* fail) {
+  double acc = 0.0;
+  for (int k0 = 0; k0 < width; k0 += kChunk) {
+    int32_t c[kChunk];
+    double g[kChunk];
+    unsigned ghost = 0;
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) c[u] = (k0 + u < width) ? col(k0 + u) : -1;
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) {
+      g[u] = 0.0;
+      if (c[u] >= 0) {
+        if (MULTI && c[u] >= a.n_owned)
+          ghost |= 1u << u;
+        else
+          g[u] = ld_coherent(p + c[u]);
+      }
+    }
+    if constexpr (MULTI) {
+      if (ghost) {
+#pragma unroll
+        for (int u = 0; u < kChunk; ++u)
+          if (ghost & (1u << u)) g[u] = wait_tag<true>(ghost_tb + c[u], want, fail, a.spin_ns);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kChunk; ++u) acc = fma((k0 + u < width) ? val(k0 + u) : 0.0, g[u], acc);
+  }
+  return acc;
+}
+
+template <bool MULTI, bool DICT>
+__global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const PdeArgs a) {
+  extern __shared__ double dyn_smem[];
+  __shared__ Scratch sh;
+  if (threadIdx.x == 0) sh.fail = 0;
+  __syncthreads();
+  u64 gen = a.gen_state[0];       // reduction generations (the same sequence in every CTA and on every rank)
+  u64 vtag = a.gen_state[1] + 1;  // tag of the ghost values published last: unique per write, continues across launches
+  if (blockIdx.x == a.n_workers) {
+    cg_reducer<MULTI, true>(a, sh, gen);
+    return;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // this CTA's contiguous run of slices; warp w owns slices s_first, s_first + 16, ... in EVERY phase
+  const int64_t per_cta = (a.n_slices + a.n_workers - 1) / a.n_workers;
+  const int64_t s_begin = min((int64_t)blockIdx.x * per_cta, a.n_slices);
+  const int64_t s_end = min(s_begin + per_cta, a.n_slices);
+  const int64_t s_first = s_begin + warp;
+  constexpr int64_t W = kWarpsPerBlock;
+  const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
+  double* const vr = a.work[VR];
+  double* const vq = a.work[VQ];
+  double* const vp = a.work[VP];   // the search direction: plain, gathered by every CTA after the barrier
+  double* const vx = a.x;
+  [[maybe_unused]] DictView D{};
+  Stager S{};
+  if constexpr (DICT) {
+    D = dict_load(a, dyn_smem);
+  } else if (a.staged) {  // per-warp stage buffers + mbarriers for the SELL slices (values + columns of a slice are contiguous)
+    char* smem = reinterpret_cast<char*>(dyn_smem);
+    S.base = smem + warp * 2 * kStageBytes;
+    S.bar[0] = smem_u32(smem + kWarpsPerBlock * 2 * kStageBytes + warp * 16);
+    S.bar[1] = S.bar[0] + 8;
+    S.count = 0;
+    if (lane == 0) {
+      mbar_init(S.bar[0], 1);
+      mbar_init(S.bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  int nstamp = 0;
+  stamp(a, nstamp);
+  int cur = 0;  // which of the two tagged ghost buffers the current search direction uses (MULTI)
+
+  // owned value of the search direction: plain store, and straight into the ghost slot of every neighbour rank that needs it
+  auto publish_p = [&](int64_t row, double v, bool slice_sends) {
+    vp[row] = v;
+    if constexpr (MULTI) {
+      if (slice_sends) {
+        for (int e = __ldg(a.send_of_row + row); e >= 0;) {
+          const SendEnt se = a.send_ents[e];
+          st_tag<true>(se.t[cur], v, vtag);
+          e = se.next;
+        }
+      }
+    }
+  };
+  // one SELL row (direct loads) times p
+  auto sell_times_p = [&](int64_t s, int64_t row) {
+    const int64_t beg = __ldg(a.slice_ptr + s);
+    const int width = (int)((__ldg(a.slice_ptr + s + 1) - beg) / kSlice);
+    return row_times_p<MULTI>(
+        a, width, [&](int k) { return __ldg(a.cols + beg + (int64_t)k * kSlice + lane); },
+        [&](int k) { return __ldg(a.A + beg + (int64_t)k * kSlice + lane); }, vp, a.tb[cur], vtag, &sh.fail);
+  };
+
+  // ---- K2 + initial residual: b = B v_ (+ dt stim) ; r = b - A x0 ; z = D^-1 r ; p = z -----------------------------
+  double acc3[3] = {0.0, 0.0, 0.0};  // r.z, norm^2 of r, norm^2 of b (chosen norm)
+  auto rhs_finish = [&](int64_t s, int64_t row, double bi, double ax0) {
+    const double di = __ldg(a.dinv + row);
+    const double ri = x0_prev ? bi - ax0 : bi;
+    const double zi = di * ri;
+    __stcg(vx + row, x0_prev ? __ldg(a.v_prev + row) : 0.0);
+    __stcg(vr + row, ri);
+    publish_p(row, zi, MULTI ? __ldg(a.slice_send + s) != 0 : false);
+    acc3[0] = fma(ri, zi, acc3[0]);
+    acc3[1] += norm_term(a.norm_type, ri, zi);
+    acc3[2] += norm_term(a.norm_type, bi, di * bi);
+  };
+  {
+    const bool staged_rhs = !DICT && a.staged && !x0_prev;
+    if (staged_rhs && lane == 0) {
+      if (s_first < s_end) S.issue(a, a.B, s_first, S.count);
+      if (s_first + W < s_end) S.issue(a, a.B, s_first + W, S.count + 1);
+    }
+    for (int64_t s = s_first; s < s_end; s += W) {
+      RowRef r;
+      r.row = s * kSlice + lane;
+      r.lane = lane;
+      r.slot = 0;
+      const bool on = r.row < a.n_owned;
+      double bi = 0.0, ax0 = 0.0;
+      if constexpr (DICT) {
+        if (on) {
+          r.beg = __ldg(a.slice_ptr + s);
+          r.width = (int)((__ldg(a.slice_ptr + s + 1) - r.beg) / kSlice);
+          dict_rhs_row(a, D, r, x0_prev, bi, ax0);
+        }
+      } else if (staged_rhs) {
+        const double sv = (on && a.has_stim) ? __ldg(a.stim_vec + r.row) : 0.0;
+        bi = staged_row<false, false>(a, S, a.B, s, s + 2 * W < s_end ? s + 2 * W : -1, lane, a.v_prev, 0, &sh.fail);
+        if (a.has_stim) bi = fma(a.dt, sv, bi);
+      } else {
+        r.beg = __ldg(a.slice_ptr + s);
+        r.width = (int)((__ldg(a.slice_ptr + s + 1) - r.beg) / kSlice);
+        rhs_row(a, r, x0_prev, bi, ax0);
+      }
+      if (on) rhs_finish(s, r.row, bi, ax0);
+    }
+  }
+  stamp(a, nstamp);
+  post<3, true>(acc3, a, gen, sh);   // also the barrier that makes p_0 visible
+  wait<3, true>(acc3, a, gen++, sh);
+  stamp(a, nstamp);
+  double rz = acc3[0];
+  double rnorm = sqrt(fabs(acc3[1]));
+  const double ttol = fmax(a.rtol * sqrt(fabs(acc3[2])), a.atol);
+  int its = 0;
+  int reason = classify(rnorm, ttol, a.atol, 0, a.max_it, false);
+  if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+  while (reason == 0) {
+    // ---- K4a: q = A p ; p.q -------------------------------------------------------------------------------------
+    double pq[1] = {0.0};
+    if constexpr (DICT) {
+      // two slices of the warp per trip: the pattern bytes, then up to 2 x 16 gathers, are in flight together
+      for (int64_t s = s_first; s < s_end; s += 2 * W) {
+        const int64_t row0 = s * kSlice + lane, row1 = (s + W) * kSlice + lane;
+        const bool on0 = row0 < a.n_owned, on1 = s + W < s_end && row1 < a.n_owned;
+        const int p0 = on0 ? (int)__ldg(a.pat + row0) : 255, p1 = on1 ? (int)__ldg(a.pat + row1) : 255;
+        const double pi0 = on0 ? __ldcg(vp + row0) : 0.0, pi1 = on1 ? __ldcg(vp + row1) : 0.0;
+        double q0 = 0.0, q1 = 0.0;
+        if (p0 != 255 && p1 != 255) {
+          const int b0 = p0 * kChunk, b1 = p1 * kChunk, w0 = D.sW[p0], w1 = D.sW[p1];
+          double g0[kChunk], g1[kChunk];
+#pragma unroll
+          for (int u = 0; u < kChunk; ++u) g0[u] = u < w0 ? ld_coherent(vp + row0 + D.sOff[b0 + u]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < kChunk; ++u) g1[u] = u < w1 ? ld_coherent(vp + row1 + D.sOff[b1 + u]) : 0.0;
+#pragma unroll
+          for (int u = 0; u < kChunk; ++u) q0 = fma(u < w0 ? D.sA[b0 + u] : 0.0, g0[u], q0);
+#pragma unroll
+          for (int u = 0; u < kChunk; ++u) q1 = fma(u < w1 ? D.sA[b1 + u] : 0.0, g1[u], q1);
+        } else {
+          auto one = [&](bool on, int pid, int64_t ss, int64_t row) {
+            if (!on) return 0.0;
+            if (pid == 255) return sell_times_p(ss, row);
+            const int b = pid * kChunk;
+            return row_times_p<false>(
+                a, D.sW[pid], [&](int k) { return (int32_t)row + D.sOff[b + k]; }, [&](int k) { return D.sA[b + k]; }, vp, nullptr, 0,
+                &sh.fail);
+          };
+          q0 = one(on0, p0, s, row0);
+          q1 = one(on1, p1, s + W, row1);
+        }
+        if (on0) {
+          __stcg(vq + row0, q0);
+          pq[0] = fma(pi0, q0, pq[0]);
+        }
+        if (on1) {
+          __stcg(vq + row1, q1);
+          pq[0] = fma(pi1, q1, pq[0]);
+        }
+      }
+    } else if (a.staged) {
+      if (lane == 0) {
+        if (s_first < s_end) S.issue(a, a.A, s_first, S.count);
+        if (s_first + W < s_end) S.issue(a, a.A, s_first + W, S.count + 1);
+      }
+      for (int64_t s = s_first; s < s_end; s += W) {
+        const int64_t row = s * kSlice + lane;
+        const bool on = row < a.n_owned;
+        const double pi = on ? __ldcg(vp + row) : 0.0;  // requested before the gathers
+        const double qi = staged_row_p<MULTI>(a, S, a.A, s, s + 2 * W < s_end ? s + 2 * W : -1, lane, vp, a.tb[cur], vtag, &sh.fail);
+        if (on) {
+          __stcg(vq + row, qi);
+          pq[0] = fma(pi, qi, pq[0]);
+        }
+      }
+    } else {
+      for (int64_t s = s_first; s < s_end; s += W) {
+        const int64_t row = s * kSlice + lane;
+        if (row < a.n_owned) {
+          const double pi = __ldcg(vp + row);
+          const double qi = sell_times_p(s, row);
+          __stcg(vq + row, qi);
+          pq[0] = fma(pi, qi, pq[0]);
+        }
+      }
+    }
+    stamp(a, nstamp);
+    post<1>(pq, a, gen, sh);
+    wait<1>(pq, a, gen++, sh);
+    stamp(a, nstamp);
+    const double alpha = rz / pq[0];
+    // ---- K4b: x += alpha p ; r -= alpha q ; z = D^-1 r ; r.z and the residual norm: four rows per trip ---------------
+    double acc2[2] = {0.0, 0.0};
+    for (int64_t s = s_first; s < s_end; s += 4 * W) {
+      double q[4], r[4], d[4], pp[4], x[4];
+      bool on[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = (s + j * W) * kSlice + lane;
+        on[j] = s + j * W < s_end && row < a.n_owned;
+        if (on[j]) {
+          q[j] = __ldcg(vq + row);
+          r[j] = __ldcg(vr + row);
+          d[j] = __ldg(a.dinv + row);
+          pp[j] = __ldcg(vp + row);
+          x[j] = __ldcg(vx + row);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (on[j]) {
+          const int64_t row = (s + j * W) * kSlice + lane;
+          const double ri = fma(-alpha, q[j], r[j]);
+          const double zi = d[j] * ri;
+          __stcg(vx + row, fma(alpha, pp[j], x[j]));
+          __stcg(vr + row, ri);
+          acc2[0] = fma(ri, zi, acc2[0]);
+          acc2[1] += norm_term(a.norm_type, ri, zi);
+        }
+      }
+    }
+    stamp(a, nstamp);
+    post<2>(acc2, a, gen, sh);
+    wait<2>(acc2, a, gen++, sh);
+    stamp(a, nstamp);
+    ++its;
+    rnorm = sqrt(fabs(acc2[1]));
+    const double beta = acc2[0] / rz;
+    rz = acc2[0];
+    reason = classify(rnorm, ttol, a.atol, its, a.max_it, !(pq[0] == pq[0]) || pq[0] == 0.0);
+    if (sh.fail) reason = MONO_KSP_DIVERGED_NAN;
+    if (reason != 0) break;
+    // ---- p = z + beta p, then the barrier that makes it visible --------------------------------------------------
+    ++vtag;
+    cur ^= 1;
+    for (int64_t s = s_first; s < s_end; s += 4 * W) {
+      double pp[4], d[4], r[4];
+      bool on[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = (s + j * W) * kSlice + lane;
+        on[j] = s + j * W < s_end && row < a.n_owned;
+        if (on[j]) {
+          pp[j] = __ldcg(vp + row);
+          d[j] = __ldg(a.dinv + row);
+          r[j] = __ldcg(vr + row);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (on[j]) {
+          const int64_t sj = s + j * W;
+          publish_p(sj * kSlice + lane, fma(beta, pp[j], d[j] * r[j]), MULTI ? __ldg(a.slice_send + sj) != 0 : false);
+        }
+      }
+    }
+    stamp(a, nstamp);
+    double one[1] = {0.0};
+    post<1, true>(one, a, gen, sh);
+    wait<1, true>(one, a, gen++, sh);
+    stamp(a, nstamp);
+  }
+  // ---- end of the solve: x is in place; ghost refresh of x (state.x.scatter_forward(), base_model.py:242) -----------
+  if constexpr (MULTI) {
+    const u64 xtag = gen;
+    for (int64_t s = s_first; s < s_end; s += W) {
+      const int64_t row = s * kSlice + lane;
+      if (row < a.n_owned && __ldg(a.slice_send + s) != 0) {
+        int e = __ldg(a.send_of_row + row);
+        if (e >= 0) {
+          const double xi = __ldcg(vx + row);
+          while (e >= 0) {
+            const SendEnt se = a.send_ents[e];
+            st_tag<true>(se.xg, xi, xtag);
+            e = se.next;
+          }
+        }
+      }
+    }
+    const int64_t n_ghost = a.n_local - a.n_owned;
+    for (int64_t g = (int64_t)blockIdx.x * kPdeThreads + threadIdx.x; g < n_ghost; g += (int64_t)a.n_workers * kPdeThreads)
+      a.x[a.n_owned + g] = wait_tag<true>(a.xg + g, xtag, &sh.fail, a.spin_ns);
+  }
+  if (sh.fail && threadIdx.x == 0) a.res->error = 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.gen_state[1] = vtag;  // every CTA read it at its start
 }
 
 // ---- KSPPIPECG: one reduction per iteration, overlapped with the SpMV -----------------------------------------
@@ -1362,7 +1780,26 @@ static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_
     c->n_pat = 0;
     return MONO_OK;
   }
-  for (int64_t r = 0; r < n; ++r) pat[(size_t)r] = (uint8_t)remap[pat[(size_t)r]];
+  // rows with a ghost column stay on the SELL path: a dictionary row gathers only from the plain owned vector
+  for (int64_t r = 0; r < n; ++r) {
+    uint8_t q = (uint8_t)remap[pat[(size_t)r]];
+    if (q != 255)
+      for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k)
+        if (indices[k] >= n) {
+          q = 255;
+          --covered;
+          break;
+        }
+    pat[(size_t)r] = q;
+  }
+  for (int64_t r : krep)
+    for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k)
+      if (indices[k] >= n) covered = 0;  // (a stencil whose representative reaches into the ghosts: no such mesh generator here)
+  c->dict_cover = (double)covered / (double)n;
+  if (c->dict_cover < 0.5) {
+    c->n_pat = 0;
+    return MONO_OK;
+  }
   const int np = (int)krep.size();
   std::vector<int32_t> off((size_t)np * kChunk, 0), w((size_t)np, 0);
   std::vector<int64_t> src((size_t)np * kChunk, -1);
@@ -1590,16 +2027,25 @@ static int pde_select_mode(mono_ctx* c) {
       c->resident_smem = 0;
     }
   }
+  // streaming KSPCG: plain vectors + fenced barrier (pde_cg_stream_kernel); MONO_PDE_TAGGED_STREAM=1 keeps the tagged
+  // exchange of the resident kernels for it (measurement / fallback)
+  c->stream_plain = !c->resident && !pipe && getenv("MONO_PDE_TAGGED_STREAM") == nullptr;
   c->dict_active = !c->resident && !pipe && c->n_pat > 0;
   if (c->dict_active) {
-    k = multi ? (const void*)pde_cg_kernel<false, false, true, true> : (const void*)pde_cg_kernel<false, false, false, true>;
+    if (c->stream_plain)
+      k = multi ? (const void*)pde_cg_stream_kernel<true, true> : (const void*)pde_cg_stream_kernel<false, true>;
+    else
+      k = multi ? (const void*)pde_cg_kernel<false, false, true, true> : (const void*)pde_cg_kernel<false, false, false, true>;
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kDictSmem) != cudaSuccess) {
       (void)cudaGetLastError();
       c->dict_active = false;
     }
   }
   if (!c->dict_active && !c->resident && !pipe && c->max_width <= kChunk && getenv("MONO_PDE_NO_STAGING") == nullptr) {
-    k = pde_kernel_for_mode(c, false, false, multi);
+    if (c->stream_plain)
+      k = multi ? (const void*)pde_cg_stream_kernel<true, false> : (const void*)pde_cg_stream_kernel<false, false>;
+    else
+      k = pde_kernel_for_mode(c, false, false, multi);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmem) == cudaSuccess)
       c->staged = true;
     else
@@ -1621,6 +2067,7 @@ static void fill_sync_args(const mono_ctx* c, PdeArgs& a) {
   a.peer_xrecs[c->rank] = c->xrecs;
   a.send_of_row = c->send_of_row_dev;
   a.send_ents = static_cast<const SendEnt*>(c->send_ents_dev);
+  a.slice_send = c->slice_send_dev;
 }
 
 static int stim_refresh(mono_ctx* c, double t_eval, int* has_stim) {
@@ -1660,11 +2107,14 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   int has_stim = 0;
   int rc = stim_refresh(c, t_eval, &has_stim);
   if (rc) return rc;
-  if (!c->resident && !c->work[0]) {  // streaming mode: thread-private vectors live in global memory
+  if (!c->resident) {  // streaming mode: thread-private vectors live in global memory (allocated on first use)
     const int64_t no = std::max<int64_t>(c->n_owned, 32);
-    for (double*& p : c->work) {
-      MONO_CUDA(c, cudaMalloc(&p, sizeof(double) * no));
-      MONO_CUDA(c, cudaMemsetAsync(p, 0, sizeof(double) * no, c->stream));
+    for (int k = 0; k < 10; ++k) {
+      const bool needed = c->stream_plain ? (k == VR || k == VQ || k == VP) : true;  // KSPCG keeps r, q, p (x, d alias a.x, a.dinv)
+      if (needed && !c->work[k]) {
+        MONO_CUDA(c, cudaMalloc(&c->work[k], sizeof(double) * no));
+        MONO_CUDA(c, cudaMemsetAsync(c->work[k], 0, sizeof(double) * no, c->stream));
+      }
     }
   }
   PdeArgs a;
@@ -1718,6 +2168,12 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
     kern = multi ? (const void*)pde_cg_kernel<false, false, true, true> : (const void*)pde_cg_kernel<false, false, false, true>;
     smem = kDictSmem;
   }
+  if (c->stream_plain) {
+    if (c->dict_active)
+      kern = multi ? (const void*)pde_cg_stream_kernel<true, true> : (const void*)pde_cg_stream_kernel<false, true>;
+    else
+      kern = multi ? (const void*)pde_cg_stream_kernel<true, false> : (const void*)pde_cg_stream_kernel<false, false>;
+  }
   MONO_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(c->pde_blocks), dim3(c->pde_threads), args, smem, c->stream));
   c->launches++;
   return MONO_OK;
@@ -1763,10 +2219,16 @@ int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std
     e.pad = 0;
     first[row[i]] = (int32_t)i;
   }
+  std::vector<uint8_t> slice_send((size_t)std::max<int64_t>(c->n_slices, 1), 0);
+  for (size_t i = 0; i < n; ++i) slice_send[(size_t)(row[i] / kSlice)] = 1;
   if (c->send_of_row_dev) cudaFree(c->send_of_row_dev);
   if (c->send_ents_dev) cudaFree(c->send_ents_dev);
+  if (c->slice_send_dev) cudaFree(c->slice_send_dev);
   c->send_of_row_dev = nullptr;
   c->send_ents_dev = nullptr;
+  c->slice_send_dev = nullptr;
+  MONO_CUDA(c, cudaMalloc(&c->slice_send_dev, slice_send.size()));
+  MONO_CUDA(c, cudaMemcpyAsync(c->slice_send_dev, slice_send.data(), slice_send.size(), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaMalloc(&c->send_of_row_dev, sizeof(int32_t) * first.size()));
   MONO_CUDA(c, cudaMalloc(&c->send_ents_dev, sizeof(SendEnt) * ents.size()));
   MONO_CUDA(c, cudaMemcpyAsync(c->send_of_row_dev, first.data(), sizeof(int32_t) * first.size(), cudaMemcpyHostToDevice, c->stream));

@@ -172,7 +172,9 @@ int mono_ctx_destroy(mono_ctx* c) {
                   (void*)c->ksp_dev, (void*)c->probes_dev,
                   (void*)c->probe_vals_dev, (void*)c->probe_act_dev, (void*)c->flush_buf, (void*)c->send_idx_dev,
                   (void*)c->send_buf, (void*)c->red_buf, (void*)c->pat_dev, (void*)c->dict_off_dev, (void*)c->dict_w_dev,
-                  (void*)c->dict_src_dev, (void*)c->dict_A_dev, (void*)c->dict_B_dev})
+                  (void*)c->dict_src_dev, (void*)c->dict_A_dev, (void*)c->dict_B_dev, (void*)c->dict_cl_dev, (void*)c->nd_rows_dev,
+                  (void*)c->nd_w_dev, (void*)c->nd_cols_dev, (void*)c->nd_src_dev, (void*)c->nd_A_dev, (void*)c->nd_B_dev,
+                  (void*)c->nd_cta_ptr_dev})
     if (p) cudaFree(p);
   for (void* p : c->stim_allocs) cudaFree(p);
   if (c->ksp_host) cudaFreeHost(c->ksp_host);

@@ -134,6 +134,22 @@ struct mono_ctx {
   int32_t* dict_w_dev = nullptr;    // [n_pat] entries per pattern
   int64_t* dict_src_dev = nullptr;  // [n_pat][16] SELL position of the representative row's entries (-1: padding)
   double *dict_A_dev = nullptr, *dict_B_dev = nullptr;  // [n_pat][16] gathered from A / B after every rebuild
+  // shared-memory ring of the dictionary SpMV (pde_cg_stream_kernel, MODE 2): the column offsets of all stencils fall
+  // into a few clusters (planes of a structured mesh); per cluster a ring of 2^ring_cap_log2 elements follows the rows
+  bool ring_ok = false;             // the offsets cluster tightly enough for the rings to fit in shared memory
+  bool ring_active = false;         // the current mode runs the ring kernel
+  int ring_ncl = 0, ring_cap_log2 = 0, ring_depth = 2;
+  int64_t ring_lo[4] = {}, ring_hi[4] = {};  // offset bounds of each cluster (inclusive)
+  int32_t* dict_cl_dev = nullptr;   // [n_pat][16] cluster of each entry
+  // rows outside the dictionary (next to a ghost layer, irregular spots) in a compact row-major side table
+  int64_t n_nd = 0;
+  std::vector<int32_t> nd_rows_host;
+  int32_t* nd_rows_dev = nullptr;   // [n_nd] row
+  int32_t* nd_w_dev = nullptr;      // [n_nd] entries
+  int32_t* nd_cols_dev = nullptr;   // [n_nd][16]
+  int64_t* nd_src_dev = nullptr;    // [n_nd][16] SELL position of each entry (-1: padding)
+  double *nd_A_dev = nullptr, *nd_B_dev = nullptr;  // [n_nd][16]
+  int64_t* nd_cta_ptr_dev = nullptr;  // [pde_workers + 1] side rows of each CTA's run of slices
   KspResult* ksp_dev = nullptr;
   KspResult* ksp_host = nullptr;  // pinned
 

@@ -51,6 +51,11 @@ constexpr int kChunk = 16;            // SELL entries of a row fetched per unrol
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
 constexpr int kMaxPat = 64;           // stencil dictionary: patterns (of at most kChunk entries) held in shared memory
 constexpr int kDictSmem = kMaxPat * kChunk * (8 + 8 + 4) + kMaxPat * 4;  // A values, B values, offsets, widths
+constexpr int kRingTile = kPdeThreads;                 // rows of one CTA trip of the ring kernel (one row per thread)
+constexpr int kRingMinDepth = 2, kRingMaxDepth = 6;    // tiles whose ring data is requested ahead of the one being computed
+constexpr int kRingStages = kRingMaxDepth + 1;         // mbarriers (one per tile in flight)
+constexpr int kMaxClusters = 4;
+constexpr int kRingTableSmem = kMaxPat * kChunk * (8 + 8 + 4 + 4) + kMaxPat * 4;  // A, B, offsets, clusters, widths
 typedef unsigned long long u64;
 
 // where one owned boundary value goes on ONE neighbour rank (peer-mapped addresses of its ghost slot)
@@ -104,6 +109,16 @@ struct PdeArgs {
   const int32_t* dict_off;          // [n_pat][kChunk] column - row
   const int32_t* dict_w;            // [n_pat]
   int n_pat;
+  // ---- shared-memory ring of the dictionary SpMV (MODE 2) and the side table of the rows outside the dictionary ----
+  const int32_t* dict_cl;           // [n_pat][kChunk] cluster of an entry
+  int ring_ncl, ring_cap_log2, ring_cl0, ring_depth;  // clusters, ring capacity, cluster of offset 0, tiles requested ahead
+  int64_t ring_lo[kMaxClusters], ring_hi[kMaxClusters];
+  const int32_t* nd_rows;           // [n_nd]
+  const int32_t* nd_w;
+  const int32_t* nd_cols;           // [n_nd][kChunk]
+  const double* nd_A;
+  const double* nd_B;
+  const int64_t* nd_cta_ptr;        // [n_workers + 1]
 };
 
 __device__ __forceinline__ void stamp(const PdeArgs& a, int& n) {
@@ -567,6 +582,7 @@ struct MatA {
 };
 
 // b = B v_ (+ dt * stimulus) and, for a non-zero initial guess x0 = v_, A x0 in the same pass.
+template <bool STIM = true>
 __device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool x0_prev, double& bi, double& ax0) {
   int dummy = 0;
   auto col = [&](int k) { return __ldg(a.cols + r.beg + (int64_t)k * kSlice + r.lane); };
@@ -584,7 +600,7 @@ __device__ __forceinline__ void rhs_row(const PdeArgs& a, const RowRef& r, bool 
     bi = b1[0];
     ax0 = 0.0;
   }
-  if (a.has_stim && r.row < a.n_owned) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
+  if (STIM && a.has_stim && r.row < a.n_owned) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
 }
 
 // ---- stencil dictionary (EXPERIMENTAL) -------------------------------------------------------------------------
@@ -630,6 +646,7 @@ __device__ __forceinline__ double dict_apply(const PdeArgs& a, const DictView& D
 }
 
 // b = B v_ (+ dt * stimulus) and, for x0 = v_, A x0 in the same pass (the dictionary version of rhs_row)
+template <bool STIM = true>
 __device__ __forceinline__ void dict_rhs_row(const PdeArgs& a, const DictView& D, const RowRef& r, bool x0_prev, double& bi, double& ax0) {
   int dummy = 0;
   const int p = (int)__ldg(a.pat + r.row);
@@ -651,7 +668,7 @@ __device__ __forceinline__ void dict_rhs_row(const PdeArgs& a, const DictView& D
     bi = b1[0];
     ax0 = 0.0;
   }
-  if (a.has_stim) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
+  if (STIM && a.has_stim) bi = fma(a.dt, __ldg(a.stim_vec + r.row), bi);
 }
 
 __device__ __forceinline__ double norm_term(int norm_type, double r, double z) {
@@ -1165,8 +1182,122 @@ __device__ __forceinline__ double row_times_p(const PdeArgs& a, int width, ColF 
   return acc;
 }
 
-template <bool MULTI, bool DICT>
+// ---- shared-memory rings for the dictionary rows (MODE 2) ----------------------------------------------------------
+// On a structured mesh the column offsets of all stencils fall into a few clusters (the planes of the mesh: for the
+// Kuhn-split box z-1, z, z+1).  A CTA sweeps its contiguous run of rows in tiles of 512 (one row per thread); for every
+// cluster a ring buffer in shared memory follows the sweep: before a tile is computed, one thread has asked the TMA
+// (cp.async.bulk, completion on an mbarrier) for the part of [tile_begin + lo_c, tile_end + hi_c] of the gathered vector
+// that is not in the ring yet - every element of the vector travels L2 -> shared memory ONCE per cluster, in bulk, two
+// tiles ahead, with no register or L1 involvement - and the 15 gathers of a row become conflict-free shared-memory loads
+// ring_c[(row + off) mod cap].  Rows outside the dictionary (next to a ghost layer; multi-GPU) are skipped here and come
+// from a compact row-major side table, thread per row.
+constexpr int kModeSell = 0, kModeDictL1 = 1, kModeRing = 2;
+
+struct RingView {
+  double* buf;         // [ncl][cap]
+  uint32_t buf_u32;    // its shared-memory address
+  uint32_t bar0;       // kRingStages mbarriers
+  unsigned count;      // tiles consumed so far in this launch (stage and parity follow from it)
+  int cap_log2;
+};
+
+// thread 0: request what tile [tile_lo, tile_hi) of rows needs and the rings do not hold yet (loaded_end: per cluster,
+// end of what was requested so far in this sweep, -1 at its start)
+__device__ __forceinline__ void ring_issue(const PdeArgs& a, const RingView& R, const double* src, int64_t n_src, unsigned stage,
+                                           int64_t tile_lo, int64_t tile_hi, int64_t (&loaded_end)[kMaxClusters]) {
+  const int64_t cap = 1ll << R.cap_log2;
+  const int64_t n_even = (n_src + 1) & ~1ll;  // (the source arrays are padded: reading one element past the end is fine)
+  int64_t lo[kMaxClusters], hi[kMaxClusters];
+  uint32_t bytes = 0;
+#pragma unroll
+  for (int c = 0; c < kMaxClusters; ++c) {
+    lo[c] = hi[c] = 0;
+    if (c < a.ring_ncl) {
+      const int64_t want_lo = max(tile_lo + a.ring_lo[c], (int64_t)0) & ~1ll;
+      const int64_t want_hi = min((int64_t)((min(tile_hi + a.ring_hi[c], n_src) + 1) & ~1ll), n_even);
+      lo[c] = loaded_end[c] < 0 ? want_lo : max(loaded_end[c], want_lo);
+      hi[c] = max(want_hi, lo[c]);
+      if (hi[c] > lo[c]) loaded_end[c] = hi[c];
+      bytes += (uint32_t)(hi[c] - lo[c]) * 8u;
+    }
+  }
+  const uint32_t bar = R.bar0 + stage * 8u;
+  mbar_expect_tx(bar, bytes);
+#pragma unroll
+  for (int c = 0; c < kMaxClusters; ++c) {
+    if (c < a.ring_ncl && hi[c] > lo[c]) {
+      const int64_t pos = lo[c] & (cap - 1);
+      const int64_t first = min(hi[c] - lo[c], cap - pos);
+      const uint32_t dst = R.buf_u32 + (uint32_t)(((int64_t)c << R.cap_log2) + pos) * 8u;
+      bulk_g2s(dst, src + lo[c], (uint32_t)first * 8u, bar);
+      if (hi[c] - lo[c] > first)
+        bulk_g2s(R.buf_u32 + (uint32_t)((int64_t)c << R.cap_log2) * 8u, src + lo[c] + first, (uint32_t)(hi[c] - lo[c] - first) * 8u, bar);
+    }
+  }
+}
+
+// Sweep of the CTA's rows [row_b, row_e) in tiles, the rings following `src`; f(row) runs once per row, after the ring
+// data of its tile has landed.  pre(row) requests the own-row data of a tile (pattern byte, ...) one tile AHEAD: it runs
+// for the first tile before the loop and for tile t+1 right before f of tile t, handing over through next()/the functor's
+// own double buffer - a dependent global load in front of every tile would otherwise cost a memory latency per tile.
+template <class PreF, class RowF>
+__device__ __forceinline__ void ring_sweep(const PdeArgs& a, RingView& R, const double* src, int64_t n_src, int64_t row_b, int64_t row_e,
+                                           PreF pre, RowF f) {
+  const int64_t ntiles = (row_e - row_b + kRingTile - 1) / kRingTile;
+  const int depth = a.ring_depth;
+  int64_t loaded_end[kMaxClusters] = {-1, -1, -1, -1};
+  if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // the vector was written with ordinary stores (other CTAs, before the barrier)
+    for (int64_t t = 0; t < min((int64_t)depth, ntiles); ++t)
+      ring_issue(a, R, src, n_src, (R.count + (unsigned)t) % (unsigned)(depth + 1), row_b + t * kRingTile,
+                 min(row_b + (t + 1) * kRingTile, row_e), loaded_end);
+  }
+  pre(row_b + threadIdx.x);
+  for (int64_t t = 0; t < ntiles; ++t) {
+    const int64_t row = row_b + t * kRingTile + threadIdx.x;
+    __syncthreads();  // everybody is done with tile t-1: the ring space of the tile about to be requested is free
+    if (threadIdx.x == 0 && t + depth < ntiles)
+      ring_issue(a, R, src, n_src, (R.count + (unsigned)depth) % (unsigned)(depth + 1), row_b + (t + depth) * kRingTile,
+                 min(row_b + (t + depth + 1) * kRingTile, row_e), loaded_end);
+    mbar_wait(R.bar0 + (R.count % (unsigned)(depth + 1)) * 8u, (R.count / (unsigned)(depth + 1)) & 1u);
+    R.count++;
+    f(row, [&]() { pre(row + kRingTile); });
+  }
+  __syncthreads();  // the rings may be re-filled (next sweep) only after the last tile was read
+}
+
+// the entries of one stencil in registers (reloaded from the shared-memory dictionary when the row's pattern changes):
+// value, and (cluster << 30) | (offset mod 2^30) in one word - the ring index only needs the low bits of row + offset
+struct PatRegs {
+  int id;
+  double v[kChunk];
+  unsigned enc[kChunk];
+};
+
+__device__ __forceinline__ void pat_load(PatRegs& P, int pid, const double* sV, const int32_t* sOff, const int32_t* sCl) {
+  P.id = pid;
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) {
+    P.v[u] = sV[pid * kChunk + u];
+    P.enc[u] = ((unsigned)sCl[pid * kChunk + u] << 30) | ((unsigned)sOff[pid * kChunk + u] & 0x3fffffffu);
+  }
+}
+
+__device__ __forceinline__ double ring_at(const double* ring, unsigned enc, unsigned r, unsigned mask, int cap_log2) {
+  return ring[((r + enc) & mask) + ((enc >> 30) << cap_log2)];
+}
+
+__device__ __forceinline__ double ring_row(const PatRegs& P, const double* ring, int64_t row, unsigned mask, int cap_log2) {
+  double acc = 0.0;
+  const unsigned r = (unsigned)row;
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) acc = fma(P.v[u], ring_at(ring, P.enc[u], r, mask, cap_log2), acc);
+  return acc;
+}
+
+template <bool MULTI, int MODE>
 __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const PdeArgs a) {
+  constexpr bool DICT = MODE != kModeSell;
   extern __shared__ double dyn_smem[];
   __shared__ Scratch sh;
   if (threadIdx.x == 0) sh.fail = 0;
@@ -1178,11 +1309,13 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
     return;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // this CTA's contiguous run of slices; warp w owns slices s_first, s_first + 16, ... in EVERY phase
+  // this CTA's contiguous run of slices; warp w owns slices s_first, s_first + 16, ... in EVERY phase, i.e. thread tid owns
+  // rows row_b + tid, row_b + 512 + tid, ...
   const int64_t per_cta = (a.n_slices + a.n_workers - 1) / a.n_workers;
   const int64_t s_begin = min((int64_t)blockIdx.x * per_cta, a.n_slices);
   const int64_t s_end = min(s_begin + per_cta, a.n_slices);
   const int64_t s_first = s_begin + warp;
+  const int64_t row_b = s_begin * kSlice, row_e = min(s_end * kSlice, a.n_owned);
   constexpr int64_t W = kWarpsPerBlock;
   const bool x0_prev = a.x0_mode == MONO_X0_PREVIOUS;
   double* const vr = a.work[VR];
@@ -1190,9 +1323,38 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
   double* const vp = a.work[VP];   // the search direction: plain, gathered by every CTA after the barrier
   double* const vx = a.x;
   [[maybe_unused]] DictView D{};
+  [[maybe_unused]] const int32_t* sCl = nullptr;
+  [[maybe_unused]] RingView R{};
   Stager S{};
-  if constexpr (DICT) {
+  if constexpr (MODE == kModeDictL1) {
     D = dict_load(a, dyn_smem);
+  } else if constexpr (MODE == kModeRing) {
+    double* sA = dyn_smem;
+    double* sB = sA + kMaxPat * kChunk;
+    int32_t* sOff = reinterpret_cast<int32_t*>(sB + kMaxPat * kChunk);
+    int32_t* sClw = sOff + kMaxPat * kChunk;
+    int32_t* sW = sClw + kMaxPat * kChunk;
+    for (int i = threadIdx.x; i < kMaxPat * kChunk; i += kPdeThreads) {
+      const bool in = i < a.n_pat * kChunk;
+      sA[i] = in ? __ldg(a.dict_A + i) : 0.0;
+      sB[i] = in ? __ldg(a.dict_B + i) : 0.0;
+      sOff[i] = in ? __ldg(a.dict_off + i) : 0;
+      sClw[i] = in ? __ldg(a.dict_cl + i) : 0;
+    }
+    for (int i = threadIdx.x; i < kMaxPat; i += kPdeThreads) sW[i] = i < a.n_pat ? __ldg(a.dict_w + i) : 0;
+    D = DictView{sA, sB, sOff, sW};
+    sCl = sClw;
+    char* ring_base = reinterpret_cast<char*>(dyn_smem) + ((kRingTableSmem + 127) / 128) * 128;
+    R.buf = reinterpret_cast<double*>(ring_base);
+    R.buf_u32 = smem_u32(ring_base);
+    R.cap_log2 = a.ring_cap_log2;
+    R.bar0 = smem_u32(ring_base + ((size_t)a.ring_ncl << a.ring_cap_log2) * 8);
+    R.count = 0;
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < kRingStages; ++k) mbar_init(R.bar0 + 8u * k, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
   } else if (a.staged) {  // per-warp stage buffers + mbarriers for the SELL slices (values + columns of a slice are contiguous)
     char* smem = reinterpret_cast<char*>(dyn_smem);
     S.base = smem + warp * 2 * kStageBytes;
@@ -1223,6 +1385,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
       }
     }
   };
+  auto sends = [&](int64_t row) { return MULTI ? __ldg(a.slice_send + row / kSlice) != 0 : false; };
   // one SELL row (direct loads) times p
   auto sell_times_p = [&](int64_t s, int64_t row) {
     const int64_t beg = __ldg(a.slice_ptr + s);
@@ -1234,18 +1397,59 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
 
   // ---- K2 + initial residual: b = B v_ (+ dt stim) ; r = b - A x0 ; z = D^-1 r ; p = z -----------------------------
   double acc3[3] = {0.0, 0.0, 0.0};  // r.z, norm^2 of r, norm^2 of b (chosen norm)
-  auto rhs_finish = [&](int64_t s, int64_t row, double bi, double ax0) {
-    const double di = __ldg(a.dinv + row);
+  auto rhs_finish = [&](int64_t row, double bi, double ax0, double di, double sv) {
+    if (a.has_stim) bi = fma(a.dt, sv, bi);
     const double ri = x0_prev ? bi - ax0 : bi;
     const double zi = di * ri;
     __stcg(vx + row, x0_prev ? __ldg(a.v_prev + row) : 0.0);
     __stcg(vr + row, ri);
-    publish_p(row, zi, MULTI ? __ldg(a.slice_send + s) != 0 : false);
+    publish_p(row, zi, sends(row));
     acc3[0] = fma(ri, zi, acc3[0]);
     acc3[1] += norm_term(a.norm_type, ri, zi);
     acc3[2] += norm_term(a.norm_type, bi, di * bi);
   };
-  {
+  if constexpr (MODE == kModeRing) {
+    // rows outside the dictionary first (side table, thread per row, entries in the SELL order)
+    for (int64_t i = __ldg(a.nd_cta_ptr + blockIdx.x) + threadIdx.x; i < __ldg(a.nd_cta_ptr + blockIdx.x + 1); i += kPdeThreads) {
+      const int64_t row = __ldg(a.nd_rows + i);
+      const int w = __ldg(a.nd_w + i);
+      double bi = 0.0, ax0 = 0.0;
+      for (int k = 0; k < w; ++k) {
+        const double g = __ldg(a.v_prev + __ldg(a.nd_cols + i * kChunk + k));
+        bi = fma(__ldg(a.nd_B + i * kChunk + k), g, bi);
+        if (x0_prev) ax0 = fma(__ldg(a.nd_A + i * kChunk + k), g, ax0);
+      }
+      rhs_finish(row, bi, ax0, __ldg(a.dinv + row), a.has_stim ? __ldg(a.stim_vec + row) : 0.0);
+    }
+    PatRegs P;
+    P.id = -1;
+    const unsigned mask = (1u << R.cap_log2) - 1u;
+    int pid = 255, pid_n = 255;
+    double di = 0.0, sv = 0.0, di_n = 0.0, sv_n = 0.0;
+    ring_sweep(
+        a, R, a.v_prev, a.n_owned, row_b, row_e,
+        [&](int64_t row) {
+          if (row < row_e) {
+            pid_n = (int)__ldg(a.pat + row);
+            di_n = __ldg(a.dinv + row);
+            sv_n = a.has_stim ? __ldg(a.stim_vec + row) : 0.0;
+          }
+        },
+        [&](int64_t row, auto prefetch_next) {
+          pid = pid_n, di = di_n, sv = sv_n;
+          prefetch_next();
+          if (row < row_e && pid != 255) {
+            if (pid != P.id) pat_load(P, pid, D.sB, D.sOff, sCl);
+            const double bi = ring_row(P, R.buf, row, mask, R.cap_log2);
+            double ax0 = 0.0;
+            if (x0_prev) {
+#pragma unroll
+              for (int u = 0; u < kChunk; ++u) ax0 = fma(D.sA[pid * kChunk + u], ring_at(R.buf, P.enc[u], (unsigned)row, mask, R.cap_log2), ax0);
+            }
+            rhs_finish(row, bi, ax0, di, sv);
+          }
+        });
+  } else {
     const bool staged_rhs = !DICT && a.staged && !x0_prev;
     if (staged_rhs && lane == 0) {
       if (s_first < s_end) S.issue(a, a.B, s_first, S.count);
@@ -1262,18 +1466,16 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
         if (on) {
           r.beg = __ldg(a.slice_ptr + s);
           r.width = (int)((__ldg(a.slice_ptr + s + 1) - r.beg) / kSlice);
-          dict_rhs_row(a, D, r, x0_prev, bi, ax0);
+          dict_rhs_row<false>(a, D, r, x0_prev, bi, ax0);
         }
       } else if (staged_rhs) {
-        const double sv = (on && a.has_stim) ? __ldg(a.stim_vec + r.row) : 0.0;
         bi = staged_row<false, false>(a, S, a.B, s, s + 2 * W < s_end ? s + 2 * W : -1, lane, a.v_prev, 0, &sh.fail);
-        if (a.has_stim) bi = fma(a.dt, sv, bi);
       } else {
         r.beg = __ldg(a.slice_ptr + s);
         r.width = (int)((__ldg(a.slice_ptr + s + 1) - r.beg) / kSlice);
-        rhs_row(a, r, x0_prev, bi, ax0);
+        rhs_row<false>(a, r, x0_prev, bi, ax0);
       }
-      if (on) rhs_finish(s, r.row, bi, ax0);
+      if (on) rhs_finish(r.row, bi, ax0, __ldg(a.dinv + r.row), a.has_stim ? __ldg(a.stim_vec + r.row) : 0.0);
     }
   }
   stamp(a, nstamp);
@@ -1289,7 +1491,36 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
   while (reason == 0) {
     // ---- K4a: q = A p ; p.q -------------------------------------------------------------------------------------
     double pq[1] = {0.0};
-    if constexpr (DICT) {
+    if constexpr (MODE == kModeRing) {
+      for (int64_t i = __ldg(a.nd_cta_ptr + blockIdx.x) + threadIdx.x; i < __ldg(a.nd_cta_ptr + blockIdx.x + 1); i += kPdeThreads) {
+        const int64_t row = __ldg(a.nd_rows + i);
+        const double qi = row_times_p<MULTI>(
+            a, __ldg(a.nd_w + i), [&](int k) { return __ldg(a.nd_cols + i * kChunk + k); },
+            [&](int k) { return __ldg(a.nd_A + i * kChunk + k); }, vp, a.tb[cur], vtag, &sh.fail);
+        __stcg(vq + row, qi);
+        pq[0] = fma(__ldcg(vp + row), qi, pq[0]);
+      }
+      const unsigned mask = (1u << R.cap_log2) - 1u;
+      int pid = 255, pid_n = 255;
+      PatRegs PA;  // (scoped to this phase: 64 registers the vector phases need for their loads in flight)
+      PA.id = -1;
+      ring_sweep(
+          a, R, vp, a.n_owned, row_b, row_e,
+          [&](int64_t row) {
+            if (row < row_e) pid_n = (int)__ldg(a.pat + row);
+          },
+          [&](int64_t row, auto prefetch_next) {
+            pid = pid_n;
+            prefetch_next();
+            if (row < row_e && pid != 255) {
+              if (pid != PA.id) pat_load(PA, pid, D.sA, D.sOff, sCl);
+              const double qi = ring_row(PA, R.buf, row, mask, R.cap_log2);
+              const double pi = R.buf[(a.ring_cl0 << R.cap_log2) + ((unsigned)row & mask)];  // the diagonal's cluster holds p[row]
+              __stcg(vq + row, qi);
+              pq[0] = fma(pi, qi, pq[0]);
+            }
+          });
+    } else if constexpr (MODE == kModeDictL1) {
       // two slices of the warp per trip: the pattern bytes, then up to 2 x 16 gathers, are in flight together
       for (int64_t s = s_first; s < s_end; s += 2 * W) {
         const int64_t row0 = s * kSlice + lane, row1 = (s + W) * kSlice + lane;
@@ -1812,14 +2043,104 @@ static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_
       src[(size_t)p * kChunk + k] = sp[(size_t)(r / kSlice)] + (int64_t)k * kSlice + (r % kSlice);
     }
   }
+  // ---- clusters of the column offsets (the planes of a structured mesh) for the shared-memory rings -----------------
+  // one ring of 2^cap_log2 elements per cluster has to hold its span plus the tiles in flight; pick the clustering (gap
+  // threshold) that needs the least shared memory
+  std::vector<int32_t> cl((size_t)np * kChunk, 0);
+  c->ring_ok = false;
+  {
+    std::vector<int64_t> offs;
+    for (int p = 0; p < np; ++p)
+      for (int k = 0; k < w[(size_t)p]; ++k) offs.push_back(off[(size_t)p * kChunk + k]);
+    std::sort(offs.begin(), offs.end());
+    offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+    size_t best_bytes = 0;
+    for (int64_t gap : {64ll, 256ll, 1024ll, 4096ll, 16384ll, 65536ll}) {
+      std::vector<std::pair<int64_t, int64_t>> cls;
+      for (int64_t o : offs) {
+        if (cls.empty() || o - cls.back().second > gap)
+          cls.emplace_back(o, o);
+        else
+          cls.back().second = o;
+      }
+      if ((int)cls.size() > kMaxClusters) continue;
+      int64_t span = 0;
+      for (auto& q : cls) span = std::max(span, q.second - q.first + 1);
+      int lg = 9;
+      while ((1ll << lg) < span + (int64_t)(kRingMinDepth + 1) * kRingTile + 4) ++lg;
+      const size_t bytes = cls.size() * ((size_t)8 << lg);
+      if (bytes + kRingTableSmem + 64 > 200 * 1024) continue;
+      if (!c->ring_ok || bytes < best_bytes) {
+        c->ring_ok = true;
+        best_bytes = bytes;
+        c->ring_ncl = (int)cls.size();
+        c->ring_cap_log2 = lg;
+        // the power of two usually leaves room for more tiles in flight than the minimum
+        c->ring_depth = (int)std::min<int64_t>(kRingMaxDepth, ((1ll << lg) - span - 4) / kRingTile - 1);
+        for (size_t q = 0; q < cls.size(); ++q) {
+          c->ring_lo[q] = cls[q].first;
+          c->ring_hi[q] = cls[q].second;
+        }
+      }
+    }
+    if (c->ring_ok) {
+      int cl0 = 0;  // cluster of offset 0 (the diagonal): padding entries point there
+      for (int q = 0; q < c->ring_ncl; ++q)
+        if (c->ring_lo[q] <= 0 && 0 <= c->ring_hi[q]) cl0 = q;
+      for (int p = 0; p < np; ++p)
+        for (int k = 0; k < kChunk; ++k) {
+          int q = cl0;
+          if (k < w[(size_t)p])
+            for (int j = 0; j < c->ring_ncl; ++j)
+              if (c->ring_lo[j] <= off[(size_t)p * kChunk + k] && off[(size_t)p * kChunk + k] <= c->ring_hi[j]) q = j;
+          cl[(size_t)p * kChunk + k] = q;
+        }
+    }
+  }
+  // ---- side table: the rows outside the dictionary, row-major (16 entries each) --------------------------------------
+  c->nd_rows_host.clear();
+  for (int64_t r = 0; r < n; ++r)
+    if (pat[(size_t)r] == 255) c->nd_rows_host.push_back((int32_t)r);
+  c->n_nd = (int64_t)c->nd_rows_host.size();
+  bool side_ok = true;
+  for (int32_t r : c->nd_rows_host)
+    if (indptr[r + 1] - indptr[r] > kChunk) side_ok = false;
+  if (!side_ok || c->n_nd > n / 4) c->ring_ok = false;  // (wide or many irregular rows: the SELL stream serves them better)
+  if (c->ring_ok && c->n_nd > 0) {
+    const size_t m = (size_t)c->n_nd;
+    std::vector<int32_t> ncols(m * kChunk), nw(m);
+    std::vector<int64_t> nsrc(m * kChunk, -1);
+    for (size_t i = 0; i < m; ++i) {
+      const int64_t r = c->nd_rows_host[i];
+      const int wd = (int)(indptr[r + 1] - indptr[r]);
+      nw[i] = wd;
+      for (int k = 0; k < kChunk; ++k) {
+        ncols[i * kChunk + k] = k < wd ? indices[indptr[r] + k] : (int32_t)r;
+        if (k < wd) nsrc[i * kChunk + k] = sp[(size_t)(r / kSlice)] + (int64_t)k * kSlice + (r % kSlice);
+      }
+    }
+    MONO_CUDA(c, cudaMalloc(&c->nd_rows_dev, m * sizeof(int32_t)));
+    MONO_CUDA(c, cudaMalloc(&c->nd_w_dev, m * sizeof(int32_t)));
+    MONO_CUDA(c, cudaMalloc(&c->nd_cols_dev, m * kChunk * sizeof(int32_t)));
+    MONO_CUDA(c, cudaMalloc(&c->nd_src_dev, m * kChunk * sizeof(int64_t)));
+    MONO_CUDA(c, cudaMalloc(&c->nd_A_dev, m * kChunk * sizeof(double)));
+    MONO_CUDA(c, cudaMalloc(&c->nd_B_dev, m * kChunk * sizeof(double)));
+    MONO_CUDA(c, cudaMemcpyAsync(c->nd_rows_dev, c->nd_rows_host.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaMemcpyAsync(c->nd_w_dev, nw.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaMemcpyAsync(c->nd_cols_dev, ncols.data(), m * kChunk * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaMemcpyAsync(c->nd_src_dev, nsrc.data(), m * kChunk * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   MONO_CUDA(c, cudaMalloc(&c->pat_dev, (size_t)n));
   MONO_CUDA(c, cudaMalloc(&c->dict_off_dev, off.size() * sizeof(int32_t)));
+  MONO_CUDA(c, cudaMalloc(&c->dict_cl_dev, cl.size() * sizeof(int32_t)));
   MONO_CUDA(c, cudaMalloc(&c->dict_w_dev, w.size() * sizeof(int32_t)));
   MONO_CUDA(c, cudaMalloc(&c->dict_src_dev, src.size() * sizeof(int64_t)));
   MONO_CUDA(c, cudaMalloc(&c->dict_A_dev, off.size() * sizeof(double)));
   MONO_CUDA(c, cudaMalloc(&c->dict_B_dev, off.size() * sizeof(double)));
   MONO_CUDA(c, cudaMemcpyAsync(c->pat_dev, pat.data(), (size_t)n, cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaMemcpyAsync(c->dict_off_dev, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  MONO_CUDA(c, cudaMemcpyAsync(c->dict_cl_dev, cl.data(), cl.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaMemcpyAsync(c->dict_w_dev, w.data(), w.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaMemcpyAsync(c->dict_src_dev, src.data(), src.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1904,6 +2225,12 @@ int pde_update_matrices(mono_ctx* c, double dt) {
     if (c->n_pat > 0) {
       dict_gather_kernel<<<1, 1024, 0, c->stream>>>(c->n_pat * kChunk, c->dict_src_dev, c->A, c->B, c->dict_A_dev, c->dict_B_dev);
       c->launches++;
+      if (c->nd_src_dev != nullptr && c->n_nd > 0) {
+        const int64_t m = c->n_nd * kChunk;
+        dict_gather_kernel<<<(int)std::min<int64_t>((m + 1023) / 1024, 4096), 1024, 0, c->stream>>>((int)m, c->nd_src_dev, c->A, c->B,
+                                                                                                c->nd_A_dev, c->nd_B_dev);
+        c->launches++;
+      }
     }
     MONO_CUDA(c, cudaGetLastError());
   }
@@ -1998,6 +2325,10 @@ static const void* pde_kernel_tbl(bool pipe, bool cheb, bool resident, bool mats
   return cheb ? (const void*)pde_pipecg_kernel<false, false, MULTI, true> : (const void*)pde_pipecg_kernel<false, false, MULTI, false>;
 }
 
+static size_t pde_ring_smem(const mono_ctx* c) {
+  return ((size_t)(kRingTableSmem + 127) / 128) * 128 + ((size_t)c->ring_ncl << c->ring_cap_log2) * 8 + kRingStages * 8 + 64;
+}
+
 static const void* pde_kernel_for_mode(const mono_ctx* c, bool resident, bool matsmem, bool multi) {
   const bool pipe = c->ksp_type == MONO_KSP_PIPECG;
   const bool cheb = pipe && c->pc_type == MONO_PC_CHEBYSHEV && c->cheb_k > 1;
@@ -2031,19 +2362,47 @@ static int pde_select_mode(mono_ctx* c) {
   // exchange of the resident kernels for it (measurement / fallback)
   c->stream_plain = !c->resident && !pipe && getenv("MONO_PDE_TAGGED_STREAM") == nullptr;
   c->dict_active = !c->resident && !pipe && c->n_pat > 0;
+  c->ring_active = false;
   if (c->dict_active) {
-    if (c->stream_plain)
-      k = multi ? (const void*)pde_cg_stream_kernel<true, true> : (const void*)pde_cg_stream_kernel<false, true>;
-    else
+    size_t smem = kDictSmem;
+    if (c->stream_plain) {
+      c->ring_active = c->ring_ok && getenv("MONO_PDE_NO_RING") == nullptr;
+      if (c->ring_active) {
+        k = multi ? (const void*)pde_cg_stream_kernel<true, kModeRing> : (const void*)pde_cg_stream_kernel<false, kModeRing>;
+        smem = pde_ring_smem(c);
+        if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+          (void)cudaGetLastError();
+          c->ring_active = false;
+          smem = kDictSmem;
+        }
+      }
+      if (!c->ring_active)
+        k = multi ? (const void*)pde_cg_stream_kernel<true, kModeDictL1> : (const void*)pde_cg_stream_kernel<false, kModeDictL1>;
+    } else {
       k = multi ? (const void*)pde_cg_kernel<false, false, true, true> : (const void*)pde_cg_kernel<false, false, false, true>;
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kDictSmem) != cudaSuccess) {
+    }
+    if (!c->ring_active && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
       (void)cudaGetLastError();
       c->dict_active = false;
+    }
+    if (c->ring_active) {  // side rows of each CTA's run of slices (same split as the kernel's)
+      const int64_t per_cta = (c->n_slices + c->pde_workers - 1) / c->pde_workers;
+      std::vector<int64_t> ptr((size_t)c->pde_workers + 1, 0);
+      for (int b = 0; b <= c->pde_workers; ++b) {
+        const int64_t row_lo = std::min<int64_t>((int64_t)b * per_cta, c->n_slices) * kSlice;
+        ptr[(size_t)b] = std::lower_bound(c->nd_rows_host.begin(), c->nd_rows_host.end(), row_lo,
+                                          [](int32_t r, int64_t v) { return (int64_t)r < v; }) - c->nd_rows_host.begin();
+      }
+      if (c->nd_cta_ptr_dev) cudaFree(c->nd_cta_ptr_dev);
+      c->nd_cta_ptr_dev = nullptr;
+      MONO_CUDA(c, cudaMalloc(&c->nd_cta_ptr_dev, ptr.size() * sizeof(int64_t)));
+      MONO_CUDA(c, cudaMemcpyAsync(c->nd_cta_ptr_dev, ptr.data(), ptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+      MONO_CUDA(c, cudaStreamSynchronize(c->stream));
     }
   }
   if (!c->dict_active && !c->resident && !pipe && c->max_width <= kChunk && getenv("MONO_PDE_NO_STAGING") == nullptr) {
     if (c->stream_plain)
-      k = multi ? (const void*)pde_cg_stream_kernel<true, false> : (const void*)pde_cg_stream_kernel<false, false>;
+      k = multi ? (const void*)pde_cg_stream_kernel<true, kModeSell> : (const void*)pde_cg_stream_kernel<false, kModeSell>;
     else
       k = pde_kernel_for_mode(c, false, false, multi);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, kStagedSmem) == cudaSuccess)
@@ -2158,6 +2517,23 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   a.dict_off = c->dict_off_dev;
   a.dict_w = c->dict_w_dev;
   a.n_pat = c->n_pat;
+  a.dict_cl = c->dict_cl_dev;
+  a.ring_ncl = c->ring_ncl;
+  a.ring_cap_log2 = c->ring_cap_log2;
+  a.ring_cl0 = 0;
+  a.ring_depth = std::max(c->ring_depth, kRingMinDepth);
+  if (const char* e = getenv("MONO_RING_DEPTH")) a.ring_depth = std::max(1, std::min(atoi(e), c->ring_depth));
+  for (int q = 0; q < kMaxClusters; ++q) {
+    a.ring_lo[q] = c->ring_lo[q];
+    a.ring_hi[q] = c->ring_hi[q];
+    if (q < c->ring_ncl && c->ring_lo[q] <= 0 && 0 <= c->ring_hi[q]) a.ring_cl0 = q;
+  }
+  a.nd_rows = c->nd_rows_dev;
+  a.nd_w = c->nd_w_dev;
+  a.nd_cols = c->nd_cols_dev;
+  a.nd_A = c->nd_A_dev;
+  a.nd_B = c->nd_B_dev;
+  a.nd_cta_ptr = c->nd_cta_ptr_dev;
   const bool multi = c->nranks > 1;
   if (multi && !c->peers_ready)
     return mono_fail(c, MONO_E_INVALID, "multi-rank context: call mono_set_halo (on every rank) before stepping the PDE stage");
@@ -2169,10 +2545,14 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
     smem = kDictSmem;
   }
   if (c->stream_plain) {
-    if (c->dict_active)
-      kern = multi ? (const void*)pde_cg_stream_kernel<true, true> : (const void*)pde_cg_stream_kernel<false, true>;
-    else
-      kern = multi ? (const void*)pde_cg_stream_kernel<true, false> : (const void*)pde_cg_stream_kernel<false, false>;
+    if (c->ring_active) {
+      kern = multi ? (const void*)pde_cg_stream_kernel<true, kModeRing> : (const void*)pde_cg_stream_kernel<false, kModeRing>;
+      smem = pde_ring_smem(c);
+    } else if (c->dict_active) {
+      kern = multi ? (const void*)pde_cg_stream_kernel<true, kModeDictL1> : (const void*)pde_cg_stream_kernel<false, kModeDictL1>;
+    } else {
+      kern = multi ? (const void*)pde_cg_stream_kernel<true, kModeSell> : (const void*)pde_cg_stream_kernel<false, kModeSell>;
+    }
   }
   MONO_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(c->pde_blocks), dim3(c->pde_threads), args, smem, c->stream));
   c->launches++;

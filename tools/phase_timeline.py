@@ -20,7 +20,11 @@ for rep in range(2):
     st = np.array(ctx.debug_timeline(True, True), dtype=np.int64)
     d = np.diff(st) / 1e3
     print("rows", n, "its", ctx.ksp_info()[0], "total us %.1f" % ((st[-1] - st[0]) / 1e3))
-    if ksp == "cg":
+    if ksp == "cg" and os.environ.get("MONO_PDE_TAGGED_STREAM") is None and not getattr(solver.pde, "_resident", False):
+        # pde_cg_stream_kernel (dictionary rows): stamps after rhs, red0, then per iteration spmv, red, axpy, red, pupd, barrier
+        names = ["rhs", "red0"] + ["spmv", "red", "axpy", "red", "pupd", "barr"] * 20
+        bytes_row = {"rhs": 49, "spmv": 25, "axpy": 56, "pupd": 32}
+    elif ksp == "cg":
         names = ["rhs", "red0"] + ["spmv", "red", "axpy", "red", "pupd"] * 20
         bytes_row = {"rhs": 244, "spmv": 212, "axpy": 56, "pupd": 48}
     else:

@@ -70,6 +70,10 @@ SIGNATURES = {
     "mono_probe_values": (C.c_int, [C.c_void_p, c_double_p]),
     "mono_probe_activation": (C.c_int, [C.c_void_p, C.c_double]),
     "mono_probe_activation_times": (C.c_int, [C.c_void_p, c_double_p]),
+    "mono_observe_config": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "mono_activation_map": (C.c_int, [C.c_void_p, c_double_p]),
+    "mono_v_minmax": (C.c_int, [C.c_void_p, c_double_p, c_double_p]),
+    "mono_get_v_strided": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, c_double_p]),
     "mono_timer_start": (C.c_int, [C.c_void_p, C.c_int]),
     "mono_timer_stop": (C.c_int, [C.c_void_p, C.c_int]),
     "mono_timer_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_float)]),
@@ -457,6 +461,24 @@ class Context:
     def probe_activation_times(self, n: int) -> np.ndarray:
         out = np.zeros(n, dtype=np.float64)
         self._ck(self.lib.mono_probe_activation_times(self.h, _dp(out)))
+        return out
+
+    def observe_config(self, activation_map: bool, threshold: float = 0.0, minmax: bool = False):
+        self._ck(self.lib.mono_observe_config(self.h, 1 if activation_map else 0, float(threshold), 1 if minmax else 0))
+
+    def activation_map(self) -> np.ndarray:
+        out = np.empty(self.n_owned, dtype=np.float64)
+        self._ck(self.lib.mono_activation_map(self.h, _dp(out)))
+        return out
+
+    def v_minmax(self) -> tuple[float, float]:
+        lo, hi = C.c_double(), C.c_double()
+        self._ck(self.lib.mono_v_minmax(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def get_v_strided(self, offset: int, stride: int, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=np.float64)
+        self._ck(self.lib.mono_get_v_strided(self.h, int(offset), int(stride), int(count), _dp(out)))
         return out
 
     # ---- measurement ----------------------------------------------------------------------------

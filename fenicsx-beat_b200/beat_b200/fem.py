@@ -1035,6 +1035,39 @@ class Separable(TimeFunction):
         self.g, self.degree = g, degree
 
 
+class WindowedField(TimeWindow):
+    """conditional(And(<x in a region>, ge(time, start), le(time, end)), amplitude, 0): a TimeWindow whose amplitude is
+    multiplied by a spatial indicator ``g(x)`` (array (gdim, n) -> 0/1).  The window test runs on the device like
+    TimeWindow's; ``g`` enters the load vector at set-up with the quadrature UFL would estimate for such a conditional
+    (degree of the true/false values + the P1 test function = 1: the centroid rule)."""
+
+    def __init__(self, time: Constant, start: float, end: float, amplitude, g: Callable[[np.ndarray], np.ndarray], degree: int = 1):
+        super().__init__(time, start, end, amplitude)
+        self.g, self.degree = g, degree
+
+    def evaluate(self, x: np.ndarray, t: float | None = None) -> np.ndarray:
+        """Value at the points x (gdim, n) at time t (default: the current value of ``time``)."""
+        t = float(self.time.value) if t is None else float(t)
+        on = self.start <= t <= self.end
+        return float(self.amplitude) * np.asarray(self.g(x), dtype=np.float64) if on else np.zeros(np.asarray(x).shape[1])
+
+
+class ExprSum:
+    """A sum of source terms (what ``a + b`` of two UFL expressions is): the model turns every term into its own stimulus."""
+
+    def __init__(self, terms):
+        self.terms = list(terms)
+
+    def __add__(self, other):
+        return ExprSum(self.terms + (other.terms if isinstance(other, ExprSum) else [other]))
+
+    def evaluate(self, x: np.ndarray, t: float | None = None) -> np.ndarray:
+        out = np.zeros(np.asarray(x).shape[1])
+        for e in self.terms:
+            out = out + e.evaluate(x, t)
+        return out
+
+
 class _Cmp:
     def __init__(self, op: str, a, b):
         self.op, self.a, self.b = op, a, b
@@ -1150,6 +1183,8 @@ def _assemble_p1_numpy(mesh: Mesh, M):
 
 
 def _gauss_simplex(d: int, degree: int):
+    if degree <= 1:  # the one-point (centroid) rule, what FFCx picks for an integrand of estimated degree <= 1
+        return np.full((1, d + 1), 1.0 / (d + 1)), np.ones(1)
     m = degree // 2 + d
     xg, wg = np.polynomial.legendre.leggauss(m)
     xg, wg = 0.5 * (xg + 1.0), 0.5 * wg

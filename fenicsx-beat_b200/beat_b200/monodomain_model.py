@@ -41,11 +41,18 @@ class Results(NamedTuple):
 def _transform_I_s(I_s, dZ: fem.Measure) -> list[Stimulus]:  # base_model.py:33-45
     if I_s is None:
         return []
+    if isinstance(I_s, fem.ExprSum):  # a + b of source expressions (stimulation.generate_random_activation)
+        return [Stimulus(expr=e, dZ=dZ) for e in I_s.terms]
     if isinstance(I_s, Stimulus):
+        if isinstance(I_s.expr, fem.ExprSum):
+            return [Stimulus(expr=e, dZ=I_s.dZ, marker=I_s.marker) for e in I_s.expr.terms]
         return [I_s]
     if isinstance(I_s, (fem.TimeWindow, fem.TimeFunction, fem.Constant, float, int)):
         return [Stimulus(expr=I_s, dZ=dZ)]
-    return list(I_s)
+    out: list[Stimulus] = []
+    for s in I_s:
+        out.extend(_transform_I_s(s, dZ))
+    return out
 
 
 class DeviceKSP:
@@ -189,8 +196,8 @@ class MonodomainModel:
         self._stim_amp: list[float] = []
         for s in self._I_s:
             expr = s.expr
-            g = expr.g if isinstance(expr, fem.Separable) else None
-            deg = expr.degree if isinstance(expr, fem.Separable) else 0
+            g = expr.g if isinstance(expr, (fem.Separable, fem.WindowedField)) else None
+            deg = expr.degree if isinstance(expr, (fem.Separable, fem.WindowedField)) else 0
             meas = s.dZ if s.dZ is not None else self.dx
             load = fem.load_vector(mesh, meas, s.marker, g, deg)
             idx = np.nonzero(load)[0].astype(np.int32)
@@ -281,6 +288,28 @@ class MonodomainModel:
 
     def track_activation(self, threshold: float = 0.0) -> None:
         self._ctx.probe_activation(threshold)
+
+    def observe(self, activation_map: bool = True, threshold: float = 0.0, minmax: bool = True) -> None:
+        """Whole-field observers evaluated on the device after every split step (same launch as the probes): per-node
+        activation times and min / max of v - what the demos compute from ``state.x.array`` on the host every step
+        (demos/niederer_benchmark.py:271-287), without moving the field."""
+        self._ctx.observe_config(activation_map, threshold, minmax)
+
+    def activation_map(self) -> np.ndarray:
+        """Start time of the first split step after which v > threshold, per owned dof (-1: not yet)."""
+        return self._ctx.activation_map()
+
+    def v_minmax(self) -> tuple[float, float]:
+        """(min, max) of v over this rank's owned dofs after the last split step."""
+        return self._ctx.v_minmax()
+
+    def state_snapshot(self, stride: int = 1, offset: int = 0, count: int | None = None) -> np.ndarray:
+        """v[offset::stride] of the owned dofs gathered on the device (coarse frames without moving the whole field)."""
+        n = self._mesh.index_map.size_local
+        if count is None:
+            count = max(0, (n - offset + stride - 1) // stride)
+        self._flush_host()
+        return self._ctx.get_v_strided(offset, stride, count)
 
     def probe_values(self) -> np.ndarray:
         return self._ctx.probe_values(getattr(self, "_n_probes", 0))

@@ -4,6 +4,8 @@ from __future__ import annotations
 
 from typing import NamedTuple
 
+import numpy as np
+
 from . import fem
 from .units import CM_PER_UNIT, PerLength
 
@@ -74,3 +76,25 @@ def define_stimulus(mesh: fem.Mesh, chi, time: fem.Constant, subdomain_data: fem
     dZ = get_dZ(mesh, subdomain_data)
     expr = fem.TimeWindow(time, start, start + duration, amp)
     return Stimulus(dZ=dZ, marker=marker, expr=expr)
+
+
+def generate_random_activation(mesh: fem.Mesh, time: fem.Constant, points: np.ndarray, delays: np.ndarray, stim_start: float = 0.0,
+                               stim_duration: float = 2.0, stim_amplitude: float = 1.0, tol: float = 1e-12) -> fem.ExprSum:
+    """Random spatio-temporal activation pattern (stimulation.py:279-363): the sum over the points of
+    ``conditional(|x - p_i|_inf <= tol  and  start + delay_i <= time <= start + duration + delay_i, amplitude, 0)``.
+    Returned as a sum of device-evaluated windows (one stimulus each); pass it as ``I_s`` or inside a ``Stimulus``."""
+    points = np.atleast_2d(np.asarray(points, dtype=np.float64)) if len(points) else np.zeros((0, 3))
+    assert len(points) == len(delays), "Points and delays must have the same length"
+    gdim = mesh.geometry.x.shape[1] if mesh.geometry.x.ndim == 2 else 3
+
+    def indicator(p):
+        def g(x):  # near(X[k], p[k], tol) for every coordinate the point has (stimulation.py:275-276)
+            ok = np.ones(np.asarray(x).shape[1], dtype=bool)
+            for k in range(min(len(p), gdim, np.asarray(x).shape[0])):
+                ok &= (x[k] >= p[k] - tol) & (x[k] <= p[k] + tol)
+            return ok.astype(np.float64)
+
+        return g
+
+    return fem.ExprSum([fem.WindowedField(time, stim_start + float(d), stim_start + stim_duration + float(d), stim_amplitude, indicator(p))
+                        for p, d in zip(points, delays)])

@@ -174,7 +174,7 @@ int mono_ctx_destroy(mono_ctx* c) {
                   (void*)c->send_buf, (void*)c->red_buf, (void*)c->pat_dev, (void*)c->dict_off_dev, (void*)c->dict_w_dev,
                   (void*)c->dict_src_dev, (void*)c->dict_A_dev, (void*)c->dict_B_dev, (void*)c->dict_cl_dev, (void*)c->nd_rows_dev,
                   (void*)c->nd_w_dev, (void*)c->nd_cols_dev, (void*)c->nd_src_dev, (void*)c->nd_A_dev, (void*)c->nd_B_dev,
-                  (void*)c->nd_cta_ptr_dev})
+                  (void*)c->nd_cta_ptr_dev, (void*)c->dict_rep_dev, (void*)c->dict_dinv_dev, (void*)c->slice_stim_dev, (void*)c->actmap_dev, (void*)c->minmax_dev, (void*)c->snap_dev})
     if (p) cudaFree(p);
   for (void* p : c->stim_allocs) cudaFree(p);
   if (c->ksp_host) cudaFreeHost(c->ksp_host);
@@ -620,7 +620,7 @@ static int split_step_impl(mono_ctx* c, double t0, double t1, double theta) {
     rc = stage_end(c, 0);
     if (rc) return rc;
   }
-  if (!c->probes_host.empty()) rc = probes_launch(c, t0);
+  if (!c->probes_host.empty() || c->actmap_enabled || c->minmax_enabled) rc = probes_launch(c, t0);
   if (c->stage_timing) c->stage_steps++;
   if (c->stage_timing && c->ev_used >= 4096) rc = drain_stage_events(c);
   return rc;
@@ -686,6 +686,70 @@ int mono_probe_activation_times(mono_ctx* c, double* times) {
     return MONO_OK;
   }
   return d2h(c, times, c->probe_act_dev, n);
+}
+
+int mono_observe_config(mono_ctx* c, int activation_map, double threshold, int minmax) {
+  MONO_CHECK(c, c->has_pde, "set matrices before configuring the observers");
+  if (activation_map && !c->actmap_dev) {
+    const int64_t n = std::max<int64_t>(c->n_owned, 1);
+    MONO_CUDA(c, cudaMalloc(&c->actmap_dev, sizeof(double) * n));
+    std::vector<double> neg((size_t)n, -1.0);
+    MONO_CUDA(c, cudaMemcpyAsync(c->actmap_dev, neg.data(), sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  if (minmax && !c->minmax_dev) {
+    MONO_CUDA(c, cudaMalloc(&c->minmax_dev, 2 * sizeof(unsigned long long)));
+    const unsigned long long init[2] = {~0ull, 0ull};
+    MONO_CUDA(c, cudaMemcpyAsync(c->minmax_dev, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  c->actmap_enabled = activation_map != 0;
+  c->actmap_threshold = threshold;
+  c->minmax_enabled = minmax != 0;
+  return MONO_OK;
+}
+
+int mono_activation_map(mono_ctx* c, double* times_owned) {
+  MONO_CHECK(c, c->has_pde && c->actmap_dev != nullptr, "activation map not enabled (mono_observe_config)");
+  MONO_CHECK(c, times_owned != nullptr || c->n_owned == 0, "times_owned is NULL");
+  if (c->n_owned == 0) return MONO_OK;
+  return d2h(c, times_owned, c->actmap_dev, c->n_owned);
+}
+
+int mono_v_minmax(mono_ctx* c, double* vmin, double* vmax) {
+  MONO_CHECK(c, c->has_pde && c->minmax_dev != nullptr, "min/max tracking not enabled (mono_observe_config)");
+  unsigned long long b[2];
+  MONO_CUDA(c, cudaMemcpyAsync(b, c->minmax_dev, sizeof(b), cudaMemcpyDeviceToHost, c->stream));
+  MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+  auto back = [](unsigned long long u) {
+    const unsigned long long bits = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    double v;
+    memcpy(&v, &bits, sizeof(v));
+    return v;
+  };
+  if (vmin) *vmin = b[0] == ~0ull ? std::numeric_limits<double>::infinity() : back(b[0]);
+  if (vmax) *vmax = b[1] == 0ull ? -std::numeric_limits<double>::infinity() : back(b[1]);
+  return MONO_OK;
+}
+
+int mono_get_v_strided(mono_ctx* c, int64_t offset, int64_t stride, int64_t count, double* out) {
+  MONO_CHECK(c, c->has_pde, "no PDE matrices");
+  MONO_CHECK(c, offset >= 0 && stride >= 1 && count >= 0, "bad offset / stride / count");
+  MONO_CHECK(c, count == 0 || offset + (count - 1) * stride < c->n_local, "strided range exceeds the local dofs");
+  MONO_CHECK(c, count == 0 || out != nullptr, "out is NULL");
+  if (count == 0) return MONO_OK;
+  if (count > c->snap_cap) {
+    if (c->snap_dev) {
+      MONO_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->snap_dev);
+      c->snap_dev = nullptr;
+    }
+    MONO_CUDA(c, cudaMalloc(&c->snap_dev, sizeof(double) * count));
+    c->snap_cap = count;
+  }
+  int rc = strided_pack_launch(c, offset, stride, count, c->snap_dev);
+  if (rc) return rc;
+  return d2h(c, out, c->snap_dev, count);
 }
 
 // -------------------------------------------------------------------------------------- measurement

@@ -141,6 +141,9 @@ struct mono_ctx {
   int ring_ncl = 0, ring_cap_log2 = 0, ring_depth = 2;
   int64_t ring_lo[4] = {}, ring_hi[4] = {};  // offset bounds of each cluster (inclusive)
   int32_t* dict_cl_dev = nullptr;   // [n_pat][16] cluster of each entry
+  int64_t* dict_rep_dev = nullptr;  // [n_pat] a row that has the stencil
+  double* dict_dinv_dev = nullptr;  // [n_pat] its Jacobi diagonal (gathered after every rebuild of A)
+  uint8_t* slice_stim_dev = nullptr;  // n_slices (+ padding): 1 where the current stim_vec is non-zero on a row of the slice
   // rows outside the dictionary (next to a ghost layer, irregular spots) in a compact row-major side table
   int64_t n_nd = 0;
   std::vector<int32_t> nd_rows_host;
@@ -165,6 +168,12 @@ struct mono_ctx {
   bool probes_dirty = true;
   bool act_enabled = false;
   double act_threshold = 0.0;
+  bool actmap_enabled = false, minmax_enabled = false;  // whole-field observers (mono_observe_config)
+  double actmap_threshold = 0.0;
+  double* actmap_dev = nullptr;          // n_owned: activation time of every owned node, -1 before
+  unsigned long long* minmax_dev = nullptr;  // [2]: order-preserving integer images of min and max v of the last step
+  double* snap_dev = nullptr;            // staging of mono_get_v_strided
+  int64_t snap_cap = 0;
 
   // ---- measurement ---------------------------------------------------------------------------
   cudaEvent_t timers[8][2] = {};
@@ -211,7 +220,8 @@ int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, c
 int pde_update_matrices(mono_ctx* c, double dt);
 int pde_launch_step(mono_ctx* c, double t_eval, double dt);
 int pde_setup_launch_config(mono_ctx* c);
-int probes_launch(mono_ctx* c, double t0);
+int probes_launch(mono_ctx* c, double t0);  // probes + whole-field observers, one launch
+int strided_pack_launch(mono_ctx* c, int64_t offset, int64_t stride, int64_t count, double* out_dev);
 int pde_bench_sync(mono_ctx* c, int n, float* us_per_sync);
 
 int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std::vector<std::vector<void*>>& dst_t,

@@ -49,13 +49,18 @@ constexpr int kPdeThreads = 512;
 constexpr int kWarpsPerBlock = kPdeThreads / 32;
 constexpr int kChunk = 16;            // SELL entries of a row fetched per unrolled batch
 constexpr int kMaxBlocks = 160;       // >= SM count: size of the reduction scratch in shared memory
-constexpr int kMaxPat = 64;           // stencil dictionary: patterns (of at most kChunk entries) held in shared memory
+constexpr int kMaxPat = 32;           // stencil dictionary: patterns (of at most kChunk entries) held in shared memory
 constexpr int kDictSmem = kMaxPat * kChunk * (8 + 8 + 4) + kMaxPat * 4;  // A values, B values, offsets, widths
-constexpr int kRingTile = kPdeThreads;                 // rows of one CTA trip of the ring kernel (one row per thread)
-constexpr int kRingMinDepth = 2, kRingMaxDepth = 6;    // tiles whose ring data is requested ahead of the one being computed
+constexpr int kRingRows = 2;                           // rows per thread and tile
+constexpr int kRingTile = kRingRows * kPdeThreads;     // rows of one CTA trip of the ring kernel
+constexpr int kRingChunk = kRingTile;                  // elements per bulk copy into a ring (rings advance in whole chunks)
+constexpr int kRingChunkLog2 = 10;
+static_assert((1 << kRingChunkLog2) == kRingChunk, "chunk size");
+constexpr int kRingMinDepth = 1, kRingMaxDepth = 6;    // tiles whose ring data is requested ahead of the one being computed
 constexpr int kRingStages = kRingMaxDepth + 1;         // mbarriers (one per tile in flight)
 constexpr int kMaxClusters = 4;
-constexpr int kRingTableSmem = kMaxPat * kChunk * (8 + 8 + 4 + 4) + kMaxPat * 4;  // A, B, offsets, clusters, widths
+constexpr int kRingTableSmem = kMaxPat * kChunk * (8 + 8 + 8) + kMaxPat * (4 + 8);  // A, B, {offset, cluster ring} pairs, widths, 1/diagonal
+constexpr int kRingStageBytes = kRingTile + kRingTile / kSlice;  // per tile in flight: its pattern bytes and the stimulus flags of its slices
 typedef unsigned long long u64;
 
 // where one owned boundary value goes on ONE neighbour rank (peer-mapped addresses of its ghost slot)
@@ -119,6 +124,9 @@ struct PdeArgs {
   const double* nd_A;
   const double* nd_B;
   const int64_t* nd_cta_ptr;        // [n_workers + 1]
+  const double* dict_dinv;          // [n_pat] Jacobi diagonal of a stencil (= dinv of any row that has it)
+  const uint8_t* slice_stim;        // per SELL slice: 1 when stim_vec is non-zero on some row of it
+  int dbg;                          // measurement only (MONO_RING_DBG): 1 = no ring requests, 2 = no ring compute, 4 = no q store
 };
 
 __device__ __forceinline__ void stamp(const PdeArgs& a, int& n) {
@@ -431,6 +439,19 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// returns a value that depends on the completed wait (ring_at takes it as an ordering token)
+__device__ __forceinline__ uint32_t mbar_wait_tok(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+  return ok;
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -1196,102 +1217,192 @@ constexpr int kModeSell = 0, kModeDictL1 = 1, kModeRing = 2;
 struct RingView {
   double* buf;         // [ncl][cap]
   uint32_t buf_u32;    // its shared-memory address
-  uint32_t bar0;       // kRingStages mbarriers
-  unsigned count;      // tiles consumed so far in this launch (stage and parity follow from it)
+  uint32_t full0;      // kRingStages mbarriers "the ring data of this tile has landed" (transaction count) ...
+  uint32_t empty0;     // ... and kRingStages mbarriers "all 16 warps are done with this tile" (one arrival per warp)
+  uint32_t stage_u32;  // kRingStages x kRingStageBytes: pattern bytes + stimulus flags of the tiles in flight
+  const uint8_t* stage_buf;
   int cap_log2;
+  int nst;             // stages in use = tiles in flight + 1
+  int stage;           // stage of the next tile to consume ...
+  unsigned parity;     // ... and the parity its mbarriers complete with (both continue from sweep to sweep)
+  unsigned tiles;      // tiles consumed so far in this launch
 };
 
-// thread 0: request what tile [tile_lo, tile_hi) of rows needs and the rings do not hold yet (loaded_end: per cluster,
-// end of what was requested so far in this sweep, -1 at its start)
-__device__ __forceinline__ void ring_issue(const PdeArgs& a, const RingView& R, const double* src, int64_t n_src, unsigned stage,
-                                           int64_t tile_lo, int64_t tile_hi, int64_t (&loaded_end)[kMaxClusters]) {
-  const int64_t cap = 1ll << R.cap_log2;
-  const int64_t n_even = (n_src + 1) & ~1ll;  // (the source arrays are padded: reading one element past the end is fine)
-  int64_t lo[kMaxClusters], hi[kMaxClusters];
-  uint32_t bytes = 0;
-#pragma unroll
-  for (int c = 0; c < kMaxClusters; ++c) {
-    lo[c] = hi[c] = 0;
-    if (c < a.ring_ncl) {
-      const int64_t want_lo = max(tile_lo + a.ring_lo[c], (int64_t)0) & ~1ll;
-      const int64_t want_hi = min((int64_t)((min(tile_hi + a.ring_hi[c], n_src) + 1) & ~1ll), n_even);
-      lo[c] = loaded_end[c] < 0 ? want_lo : max(loaded_end[c], want_lo);
-      hi[c] = max(want_hi, lo[c]);
-      if (hi[c] > lo[c]) loaded_end[c] = hi[c];
-      bytes += (uint32_t)(hi[c] - lo[c]) * 8u;
-    }
-  }
-  const uint32_t bar = R.bar0 + stage * 8u;
-  mbar_expect_tx(bar, bytes);
-#pragma unroll
-  for (int c = 0; c < kMaxClusters; ++c) {
-    if (c < a.ring_ncl && hi[c] > lo[c]) {
-      const int64_t pos = lo[c] & (cap - 1);
-      const int64_t first = min(hi[c] - lo[c], cap - pos);
-      const uint32_t dst = R.buf_u32 + (uint32_t)(((int64_t)c << R.cap_log2) + pos) * 8u;
-      bulk_g2s(dst, src + lo[c], (uint32_t)first * 8u, bar);
-      if (hi[c] - lo[c] > first)
-        bulk_g2s(R.buf_u32 + (uint32_t)((int64_t)c << R.cap_log2) * 8u, src + lo[c] + first, (uint32_t)(hi[c] - lo[c] - first) * 8u, bar);
-    }
-  }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Sweep of the CTA's rows [row_b, row_e) in tiles, the rings following `src`; f(row) runs once per row, after the ring
-// data of its tile has landed.  pre(row) requests the own-row data of a tile (pattern byte, ...) one tile AHEAD: it runs
-// for the first tile before the loop and for tile t+1 right before f of tile t, handing over through next()/the functor's
-// own double buffer - a dependent global load in front of every tile would otherwise cost a memory latency per tile.
-template <class PreF, class RowF>
-__device__ __forceinline__ void ring_sweep(const PdeArgs& a, RingView& R, const double* src, int64_t n_src, int64_t row_b, int64_t row_e,
-                                           PreF pre, RowF f) {
-  const int64_t ntiles = (row_e - row_b + kRingTile - 1) / kRingTile;
-  const int depth = a.ring_depth;
-  int64_t loaded_end[kMaxClusters] = {-1, -1, -1, -1};
-  if (threadIdx.x == 0) {
-    asm volatile("fence.proxy.async.global;" ::: "memory");  // the vector was written with ordinary stores (other CTAs, before the barrier)
-    for (int64_t t = 0; t < min((int64_t)depth, ntiles); ++t)
-      ring_issue(a, R, src, n_src, (R.count + (unsigned)t) % (unsigned)(depth + 1), row_b + t * kRingTile,
-                 min(row_b + (t + 1) * kRingTile, row_e), loaded_end);
+// Requests for the ring data of tile j of a sweep, in 256-element chunks (256-aligned, ring capacity a multiple of 256: a
+// chunk never wraps).  Stateless: what tile j adds to cluster c is [ceil256(need(j-1)), ceil256(need(j))) with
+// need(j) = tile_end(j) + hi_c (tile 0 starts at floor256(row_b + lo_c)), so ANY thread can issue any chunk.  That matters:
+// a cp.async.bulk costs its issuing thread several hundred cycles (measured: with one requesting thread the whole sweep
+// ran at exactly the issue rate of that thread, ~3000 cycles per tile whatever the prefetch depth), so the chunks of a tile
+// are dealt over the 16 warps - lane 0 of warp w issues chunk k of cluster c when (5 c + k) mod 16 == w and then arrives on
+// the tile's full barrier (16 arrivals) with the bytes it asked for.
+__device__ __forceinline__ void ring_issue_share(const PdeArgs& a, const RingView& R, const double* src, int64_t n_even, int stage,
+                                                 int64_t row_b, int64_t row_e, int64_t j, int warp, bool wait_empty, unsigned empty_parity) {
+  const uint32_t bar = R.full0 + (uint32_t)stage * 8u;
+  const int64_t mask = (1ll << R.cap_log2) - 1;
+  const int64_t tile_hi = min(row_b + (j + 1) * kRingTile, row_e), prev_hi = min(row_b + j * kRingTile, row_e);
+  uint32_t bytes = 0;
+  bool waited = !wait_empty;
+#pragma unroll
+  for (int c = 0; c < kMaxClusters; ++c) {
+    if (c < a.ring_ncl) {
+      const int64_t end = (min(tile_hi + a.ring_hi[c], n_even) + kRingChunk - 1) & ~(int64_t)(kRingChunk - 1);
+      const int64_t beg = j == 0 ? ((row_b + a.ring_lo[c]) >> kRingChunkLog2) << kRingChunkLog2
+                                 : (min(prev_hi + a.ring_hi[c], n_even) + kRingChunk - 1) & ~(int64_t)(kRingChunk - 1);
+      const int64_t nch = end > beg ? (end - beg) >> kRingChunkLog2 : 0;
+      for (int64_t k = (a.dbg & 8) ? (warp == 0 ? 0 : nch) : ((warp - 5 * c) & 15); k < nch; k += (a.dbg & 8) ? 1 : 16) {
+        const int64_t lo = max(beg + k * kRingChunk, (int64_t)0), hi = min(beg + (k + 1) * kRingChunk, n_even);
+        if (hi > lo && !((a.dbg & 1) && src != a.v_prev)) {
+          if (!waited) {  // the ring space this chunk overwrites was read by tile (j - stages): wait until all warps are done with it
+            mbar_wait(R.empty0 + (uint32_t)stage * 8u, empty_parity);
+            waited = true;
+          }
+          bulk_g2s(R.buf_u32 + (uint32_t)((((int64_t)c << R.cap_log2) + (lo & mask)) * 8), src + lo, (uint32_t)(hi - lo) * 8u, bar);
+          bytes += (uint32_t)(hi - lo) * 8u;
+        }
+      }
+    }
   }
-  pre(row_b + threadIdx.x);
+  if (warp == kWarpsPerBlock - 1) {  // the tile's pattern bytes and stimulus flags (buffers of this stage: same hand-shake)
+    if (!waited) mbar_wait(R.empty0 + (uint32_t)stage * 8u, empty_parity);
+    const int64_t tile_lo = row_b + j * kRingTile;  // (a multiple of the tile: the CTA's run of slices starts on a multiple of 32)
+    bulk_g2s(R.stage_u32 + (uint32_t)stage * kRingStageBytes, a.pat + tile_lo, kRingTile, bar);
+    bytes += kRingTile;
+    if (a.has_stim && src == a.v_prev) {  // (only the right-hand side needs the stimulus flags, and only while a stimulus is on)
+      bulk_g2s(R.stage_u32 + (uint32_t)stage * kRingStageBytes + kRingTile, a.slice_stim + tile_lo / kSlice, kRingTile / kSlice, bar);
+      bytes += kRingTile / kSlice;
+    }
+  }
+  mbar_expect_tx(bar, bytes);  // (arrives too: the phase cannot complete before all 16 warps have, whatever has landed already)
+}
+
+// Sweep of the CTA's rows [row_b, row_e) in tiles, the rings following `src`; f(row, tok, pid, stim_flag) runs once per row
+// after the data of its tile has landed: ring elements, the row's pattern byte and its slice's stimulus flag all arrive
+// through bulk copies on the tile's full barrier, so the consumer path has NO global load in front of its compute (a
+// per-tile dependent global load - even one requested several tiles ahead into a register queue, whose shifting moves
+// wait for the loads - costs a memory latency per tile: measured, 29 % of all stall samples on one branch).
+// The 16 warps are NOT synchronised per tile: a warp takes the next tile as soon as ITS data is there (full barrier) and
+// says so when it is done (empty barrier); a warp that has a chunk to request waits for the tile whose ring space the
+// chunk overwrites, `depth + 1` tiles back.
+template <class RowF>
+__device__ __forceinline__ void ring_sweep(const PdeArgs& a, RingView& R, const double* src, int64_t n_src, int64_t row_b, int64_t row_e,
+                                           RowF f) {
+  const int64_t ntiles = (row_e - row_b + kRingTile - 1) / kRingTile;
+  const int64_t n_even = (n_src + 1) & ~1ll;  // (the source arrays are padded: reading one element past the end is fine)
+  const int depth = R.nst - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int pstage = R.stage;            // requests (lane 0 of every warp): stage, parity and launch-wide index of the next tile to request
+  unsigned pparity = R.parity, ptile = R.tiles;
+  // Steady state (whole tiles after the first): every cluster advances by exactly one chunk per tile, chunk c =
+  // [E0_c - 1024 + 1024 j, + 1024) with E0_c the chunk-aligned end of what tile 0 needs; warp c requests it and the last
+  // warp the tile's pattern bytes - a compare or two and one bulk copy per warp and tile.  The request path must be cheap
+  // and the copies FEW: measured, a sweep costs ~0.2-0.4 us per bulk copy and SM whatever its size (8 copies of <= 2 KB per
+  // 512 rows: 1.6 us per tile even with compute and stores switched off), hence 1024-row tiles and 8 KB chunks.
+  // Tile 0 and a partial last tile take the general path.
+  const int cl = warp;
+  const bool has_chunk = warp < a.ring_ncl;
+  const int64_t chunk0 = has_chunk ? ((min(row_b + kRingTile, row_e) + a.ring_hi[cl] + kRingChunk - 1) & ~(int64_t)(kRingChunk - 1)) -
+                                         kRingTile
+                                   : 0;
+  const uint32_t ring_c = R.buf_u32 + (uint32_t)(((int64_t)cl << R.cap_log2) * 8);
+  const uint32_t pos_mask = (1u << R.cap_log2) - 1u;
+  const int64_t full_tiles = (row_e - row_b) / kRingTile;
+  auto request = [&](int64_t j) {
+    if (j >= 1 && j < full_tiles) {
+      const uint32_t bar = R.full0 + (uint32_t)pstage * 8u;
+      uint32_t bytes = 0;
+      const bool wait_empty = ptile >= (unsigned)R.nst;
+      if (has_chunk) {
+        const int64_t lo = chunk0 + j * kRingTile;
+        if (lo >= 0 && lo < n_even) {
+          if (wait_empty) mbar_wait(R.empty0 + (uint32_t)pstage * 8u, pparity ^ 1u);
+          bytes = (uint32_t)min((int64_t)kRingChunk, n_even - lo) * 8u;
+          bulk_g2s(ring_c + (((uint32_t)lo & pos_mask) << 3), src + lo, bytes, bar);
+        }
+      } else if (warp == kWarpsPerBlock - 1) {
+        if (wait_empty) mbar_wait(R.empty0 + (uint32_t)pstage * 8u, pparity ^ 1u);
+        const int64_t tile_lo = row_b + j * kRingTile;
+        bulk_g2s(R.stage_u32 + (uint32_t)pstage * kRingStageBytes, a.pat + tile_lo, kRingTile, bar);
+        bytes = kRingTile;
+        if (a.has_stim && src == a.v_prev) {
+          bulk_g2s(R.stage_u32 + (uint32_t)pstage * kRingStageBytes + kRingTile, a.slice_stim + tile_lo / kSlice, kRingTile / kSlice, bar);
+          bytes += kRingTile / kSlice;
+        }
+      }
+      mbar_expect_tx(bar, bytes);
+    } else {
+      ring_issue_share(a, R, src, n_even, pstage, row_b, row_e, j, warp, ptile >= (unsigned)R.nst, pparity ^ 1u);
+    }
+    ++ptile;
+    if (++pstage == R.nst) {
+      pstage = 0;
+      pparity ^= 1u;
+    }
+  };
+  if (lane == 0) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");  // the vector was written with ordinary stores (other CTAs, before the barrier)
+    for (int64_t t = 0; t < min((int64_t)depth, ntiles); ++t) request(t);
+  }
   for (int64_t t = 0; t < ntiles; ++t) {
     const int64_t row = row_b + t * kRingTile + threadIdx.x;
-    __syncthreads();  // everybody is done with tile t-1: the ring space of the tile about to be requested is free
-    if (threadIdx.x == 0 && t + depth < ntiles)
-      ring_issue(a, R, src, n_src, (R.count + (unsigned)depth) % (unsigned)(depth + 1), row_b + (t + depth) * kRingTile,
-                 min(row_b + (t + depth + 1) * kRingTile, row_e), loaded_end);
-    mbar_wait(R.bar0 + (R.count % (unsigned)(depth + 1)) * 8u, (R.count / (unsigned)(depth + 1)) & 1u);
-    R.count++;
-    f(row, [&]() { pre(row + kRingTile); });
+    if (lane == 0 && t + depth < ntiles) request(t + depth);
+    __syncwarp();
+    const unsigned tok = mbar_wait_tok(R.full0 + (uint32_t)R.stage * 8u, R.parity);
+    const uint8_t* st = R.stage_buf + R.stage * kRingStageBytes;
+#pragma unroll
+    for (int k = 0; k < kRingRows; ++k)  // thread tid owns rows tile + tid, tile + 512 + tid (as in the vector phases)
+      f(row + k * kPdeThreads, tok, (int)st[k * kPdeThreads + threadIdx.x], (int)st[kRingTile + k * kWarpsPerBlock + warp]);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(R.empty0 + (uint32_t)R.stage * 8u);
+    ++R.tiles;
+    if (++R.stage == R.nst) {
+      R.stage = 0;
+      R.parity ^= 1u;
+    }
   }
   __syncthreads();  // the rings may be re-filled (next sweep) only after the last tile was read
 }
 
-// the entries of one stencil in registers (reloaded from the shared-memory dictionary when the row's pattern changes):
-// value, and (cluster << 30) | (offset mod 2^30) in one word - the ring index only needs the low bits of row + offset
+// the values of one stencil in registers (reloaded from the shared-memory dictionary when the row's pattern changes); the
+// ring positions come from a table of {offset, byte offset of the cluster's ring} pairs, two per (broadcast) 16-byte load:
+// address = cluster + ((row + offset) & mask) * 8 - three integer instructions per entry.  All table words, then all ring
+// loads, are issued before the multiply-add chain starts (the chain keeps the entry order of the SELL row: same bits).
 struct PatRegs {
   int id;
   double v[kChunk];
-  unsigned enc[kChunk];
 };
 
-__device__ __forceinline__ void pat_load(PatRegs& P, int pid, const double* sV, const int32_t* sOff, const int32_t* sCl) {
+__device__ __forceinline__ void pat_load(PatRegs& P, int pid, const double* sV) {
   P.id = pid;
 #pragma unroll
-  for (int u = 0; u < kChunk; ++u) {
-    P.v[u] = sV[pid * kChunk + u];
-    P.enc[u] = ((unsigned)sCl[pid * kChunk + u] << 30) | ((unsigned)sOff[pid * kChunk + u] & 0x3fffffffu);
-  }
+  for (int u = 0; u < kChunk; ++u) P.v[u] = sV[pid * kChunk + u];
 }
 
-__device__ __forceinline__ double ring_at(const double* ring, unsigned enc, unsigned r, unsigned mask, int cap_log2) {
-  return ring[((r + enc) & mask) + ((enc >> 30) << cap_log2)];
+// (not `asm volatile`: volatile asm statements keep their order, which would serialise the 16 loads of a row behind each
+// other's address arithmetic; `tok` - a value the wait on the tile's full barrier produced - is what keeps the load after it)
+__device__ __forceinline__ double ring_at(uint32_t ring_u32, uint2 e, unsigned r, unsigned mask, unsigned tok) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(ring_u32 + e.y + (((r + e.x) & mask) << 3)), "r"(tok));
+  return v;
 }
 
-__device__ __forceinline__ double ring_row(const PatRegs& P, const double* ring, int64_t row, unsigned mask, int cap_log2) {
-  double acc = 0.0;
+__device__ __forceinline__ double ring_row(const PatRegs& P, const uint4* sEnc, uint32_t ring_u32, int64_t row, unsigned mask, unsigned tok) {
   const unsigned r = (unsigned)row;
+  uint4 e[kChunk / 2];
 #pragma unroll
-  for (int u = 0; u < kChunk; ++u) acc = fma(P.v[u], ring_at(ring, P.enc[u], r, mask, cap_log2), acc);
+  for (int u2 = 0; u2 < kChunk / 2; ++u2) e[u2] = sEnc[P.id * (kChunk / 2) + u2];
+  double g[kChunk];
+#pragma unroll
+  for (int u2 = 0; u2 < kChunk / 2; ++u2) {
+    g[2 * u2] = ring_at(ring_u32, make_uint2(e[u2].x, e[u2].y), r, mask, tok);
+    g[2 * u2 + 1] = ring_at(ring_u32, make_uint2(e[u2].z, e[u2].w), r, mask, tok);
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int u = 0; u < kChunk; ++u) acc = fma(P.v[u], g[u], acc);
   return acc;
 }
 
@@ -1311,7 +1422,10 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // this CTA's contiguous run of slices; warp w owns slices s_first, s_first + 16, ... in EVERY phase, i.e. thread tid owns
   // rows row_b + tid, row_b + 512 + tid, ...
-  const int64_t per_cta = (a.n_slices + a.n_workers - 1) / a.n_workers;
+  // (a whole number of ring tiles per CTA, so that every tile starts on a multiple of the tile size; the same split in
+  // every mode, so that the modes add their dot products in the same order and agree bit for bit)
+  int64_t per_cta = (a.n_slices + a.n_workers - 1) / a.n_workers;
+  per_cta = (per_cta + kRingTile / kSlice - 1) / (kRingTile / kSlice) * (kRingTile / kSlice);
   const int64_t s_begin = min((int64_t)blockIdx.x * per_cta, a.n_slices);
   const int64_t s_end = min(s_begin + per_cta, a.n_slices);
   const int64_t s_first = s_begin + warp;
@@ -1323,7 +1437,8 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
   double* const vp = a.work[VP];   // the search direction: plain, gathered by every CTA after the barrier
   double* const vx = a.x;
   [[maybe_unused]] DictView D{};
-  [[maybe_unused]] const int32_t* sCl = nullptr;
+  [[maybe_unused]] const uint4* sEnc = nullptr;
+  [[maybe_unused]] const double* sDinv = nullptr;
   [[maybe_unused]] RingView R{};
   Stager S{};
   if constexpr (MODE == kModeDictL1) {
@@ -1331,27 +1446,41 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
   } else if constexpr (MODE == kModeRing) {
     double* sA = dyn_smem;
     double* sB = sA + kMaxPat * kChunk;
-    int32_t* sOff = reinterpret_cast<int32_t*>(sB + kMaxPat * kChunk);
-    int32_t* sClw = sOff + kMaxPat * kChunk;
-    int32_t* sW = sClw + kMaxPat * kChunk;
+    uint2* sEncw = reinterpret_cast<uint2*>(sB + kMaxPat * kChunk);
+    double* sDinvw = reinterpret_cast<double*>(sEncw + kMaxPat * kChunk);
+    int32_t* sW = reinterpret_cast<int32_t*>(sDinvw + kMaxPat);
     for (int i = threadIdx.x; i < kMaxPat * kChunk; i += kPdeThreads) {
       const bool in = i < a.n_pat * kChunk;
       sA[i] = in ? __ldg(a.dict_A + i) : 0.0;
       sB[i] = in ? __ldg(a.dict_B + i) : 0.0;
-      sOff[i] = in ? __ldg(a.dict_off + i) : 0;
-      sClw[i] = in ? __ldg(a.dict_cl + i) : 0;
+      sEncw[i] = in ? make_uint2((unsigned)__ldg(a.dict_off + i), ((unsigned)__ldg(a.dict_cl + i) << a.ring_cap_log2) * 8u)
+                    : make_uint2(0u, (unsigned)(a.ring_cl0 << a.ring_cap_log2) * 8u);
     }
-    for (int i = threadIdx.x; i < kMaxPat; i += kPdeThreads) sW[i] = i < a.n_pat ? __ldg(a.dict_w + i) : 0;
-    D = DictView{sA, sB, sOff, sW};
-    sCl = sClw;
+    for (int i = threadIdx.x; i < kMaxPat; i += kPdeThreads) {
+      sW[i] = i < a.n_pat ? __ldg(a.dict_w + i) : 0;
+      sDinvw[i] = i < a.n_pat ? __ldg(a.dict_dinv + i) : 0.0;
+    }
+    D = DictView{sA, sB, nullptr, sW};
+    sEnc = reinterpret_cast<const uint4*>(sEncw);
+    sDinv = sDinvw;
     char* ring_base = reinterpret_cast<char*>(dyn_smem) + ((kRingTableSmem + 127) / 128) * 128;
     R.buf = reinterpret_cast<double*>(ring_base);
     R.buf_u32 = smem_u32(ring_base);
     R.cap_log2 = a.ring_cap_log2;
-    R.bar0 = smem_u32(ring_base + ((size_t)a.ring_ncl << a.ring_cap_log2) * 8);
-    R.count = 0;
+    char* after = ring_base + ((size_t)a.ring_ncl << a.ring_cap_log2) * 8;
+    R.full0 = smem_u32(after);
+    R.empty0 = R.full0 + 8u * kRingStages;
+    R.stage_buf = reinterpret_cast<const uint8_t*>(after + 2 * 8 * kRingStages);
+    R.stage_u32 = smem_u32(R.stage_buf);
+    R.nst = a.ring_depth + 1;
+    R.stage = 0;
+    R.parity = 0;
+    R.tiles = 0;
     if (threadIdx.x == 0) {
-      for (int k = 0; k < kRingStages; ++k) mbar_init(R.bar0 + 8u * k, 1);
+      for (int k = 0; k < kRingStages; ++k) {
+        mbar_init(R.full0 + 8u * k, kWarpsPerBlock);   // every warp arrives with the bytes of the chunks it requested
+        mbar_init(R.empty0 + 8u * k, kWarpsPerBlock);  // every warp arrives when it is done reading the tile
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -1424,31 +1553,20 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
     PatRegs P;
     P.id = -1;
     const unsigned mask = (1u << R.cap_log2) - 1u;
-    int pid = 255, pid_n = 255;
-    double di = 0.0, sv = 0.0, di_n = 0.0, sv_n = 0.0;
-    ring_sweep(
-        a, R, a.v_prev, a.n_owned, row_b, row_e,
-        [&](int64_t row) {
-          if (row < row_e) {
-            pid_n = (int)__ldg(a.pat + row);
-            di_n = __ldg(a.dinv + row);
-            sv_n = a.has_stim ? __ldg(a.stim_vec + row) : 0.0;
-          }
-        },
-        [&](int64_t row, auto prefetch_next) {
-          pid = pid_n, di = di_n, sv = sv_n;
-          prefetch_next();
-          if (row < row_e && pid != 255) {
-            if (pid != P.id) pat_load(P, pid, D.sB, D.sOff, sCl);
-            const double bi = ring_row(P, R.buf, row, mask, R.cap_log2);
-            double ax0 = 0.0;
-            if (x0_prev) {
+    ring_sweep(a, R, a.v_prev, a.n_owned, row_b, row_e, [&](int64_t row, unsigned tok, int pid, int stim_flag) {
+      if (row < row_e && pid != 255) {
+        if (pid != P.id) pat_load(P, pid, D.sB);
+        const double bi = ring_row(P, sEnc, R.buf_u32, row, mask, tok);
+        double ax0 = 0.0;
+        if (x0_prev) {
+          const uint2* e = reinterpret_cast<const uint2*>(sEnc) + pid * kChunk;
 #pragma unroll
-              for (int u = 0; u < kChunk; ++u) ax0 = fma(D.sA[pid * kChunk + u], ring_at(R.buf, P.enc[u], (unsigned)row, mask, R.cap_log2), ax0);
-            }
-            rhs_finish(row, bi, ax0, di, sv);
-          }
-        });
+          for (int u = 0; u < kChunk; ++u) ax0 = fma(D.sA[pid * kChunk + u], ring_at(R.buf_u32, e[u], (unsigned)row, mask, tok), ax0);
+        }
+        // the Jacobi diagonal of a dictionary row is a property of its stencil; stim_vec is read only where it is non-zero
+        rhs_finish(row, bi, ax0, sDinv[pid], (a.has_stim && stim_flag) ? __ldg(a.stim_vec + row) : 0.0);
+      }
+    });
   } else {
     const bool staged_rhs = !DICT && a.staged && !x0_prev;
     if (staged_rhs && lane == 0) {
@@ -1501,25 +1619,17 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
         pq[0] = fma(__ldcg(vp + row), qi, pq[0]);
       }
       const unsigned mask = (1u << R.cap_log2) - 1u;
-      int pid = 255, pid_n = 255;
-      PatRegs PA;  // (scoped to this phase: 64 registers the vector phases need for their loads in flight)
+      PatRegs PA;  // (scoped to this phase: registers the vector phases need for their loads in flight)
       PA.id = -1;
-      ring_sweep(
-          a, R, vp, a.n_owned, row_b, row_e,
-          [&](int64_t row) {
-            if (row < row_e) pid_n = (int)__ldg(a.pat + row);
-          },
-          [&](int64_t row, auto prefetch_next) {
-            pid = pid_n;
-            prefetch_next();
-            if (row < row_e && pid != 255) {
-              if (pid != PA.id) pat_load(PA, pid, D.sA, D.sOff, sCl);
-              const double qi = ring_row(PA, R.buf, row, mask, R.cap_log2);
-              const double pi = R.buf[(a.ring_cl0 << R.cap_log2) + ((unsigned)row & mask)];  // the diagonal's cluster holds p[row]
-              __stcg(vq + row, qi);
-              pq[0] = fma(pi, qi, pq[0]);
-            }
-          });
+      ring_sweep(a, R, vp, a.n_owned, row_b, row_e, [&](int64_t row, unsigned tok, int pid, int) {
+        if (row < row_e && pid != 255) {
+          if (pid != PA.id) pat_load(PA, pid, D.sA);
+          const double qi = (a.dbg & 2) ? 1.0 : ring_row(PA, sEnc, R.buf_u32, row, mask, tok);
+          const double pi = R.buf[(a.ring_cl0 << R.cap_log2) + ((unsigned)row & mask)];  // the diagonal's cluster holds p[row]
+          if (!(a.dbg & 4)) __stcg(vq + row, qi);
+          pq[0] = fma(pi, qi, pq[0]);
+        }
+      });
     } else if constexpr (MODE == kModeDictL1) {
       // two slices of the warp per trip: the pattern bytes, then up to 2 x 16 gathers, are in flight together
       for (int64_t s = s_first; s < s_end; s += 2 * W) {
@@ -1603,7 +1713,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
         if (on[j]) {
           q[j] = __ldcg(vq + row);
           r[j] = __ldcg(vr + row);
-          d[j] = __ldg(a.dinv + row);
+          d[j] = __ldcg(a.dinv + row);
           pp[j] = __ldcg(vp + row);
           x[j] = __ldcg(vx + row);
         }
@@ -1644,7 +1754,7 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_cg_stream_kernel(const Pde
         on[j] = s + j * W < s_end && row < a.n_owned;
         if (on[j]) {
           pp[j] = __ldcg(vp + row);
-          d[j] = __ldg(a.dinv + row);
+          d[j] = __ldcg(a.dinv + row);
           r[j] = __ldcg(vr + row);
         }
       }
@@ -1935,6 +2045,11 @@ __global__ void dict_gather_kernel(int n, const int64_t* __restrict__ src, const
   }
 }
 
+__global__ void dict_dinv_kernel(int n, const int64_t* __restrict__ rep, const double* __restrict__ dinv, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dinv[rep[i]];
+}
+
 __global__ void jacobi_kernel(int64_t n_owned, int64_t n_slices, const int64_t* __restrict__ slice_ptr,
                               const int32_t* __restrict__ cols, const double* __restrict__ A,
                               double* __restrict__ dinv, int pc_type, unsigned long long* __restrict__ gersh) {
@@ -1960,27 +2075,64 @@ __global__ void jacobi_kernel(int64_t n_owned, int64_t n_slices, const int64_t* 
 }
 
 // stim_vec[idx[e]] (+)= scale * val[e]   (scale == 0: clear the entries of a stimulus that went inactive)
+// (slice_flag: per SELL slice, set where an active stimulus touches a row - the ring kernel reads stim_vec only there)
 __global__ void stim_scatter_kernel(int64_t nnz, const int32_t* __restrict__ idx, const double* __restrict__ val,
-                                    double scale, double* __restrict__ stim_vec) {
+                                    double scale, double* __restrict__ stim_vec, uint8_t* __restrict__ slice_flag) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) {
-    if (scale == 0.0)
+    if (scale == 0.0) {
       stim_vec[idx[e]] = 0.0;
-    else
+    } else {
       atomicAdd(stim_vec + idx[e], scale * val[e]);
+      slice_flag[idx[e] / kSlice] = 1;
+    }
   }
 }
 
-__global__ void probes_kernel(int n_probes, const ProbeDev* __restrict__ probes, const double* __restrict__ x,
-                              double* __restrict__ vals, double* __restrict__ act, int act_enabled,
-                              double threshold, double t0) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_probes) return;
-  const ProbeDev pr = probes[p];
-  double v = 0.0;
-  for (int k = 0; k < pr.n; ++k) v = fma(pr.w[k], x[pr.node[k]], v);
-  vals[p] = v;
-  if (act_enabled && act[p] < 0.0 && v > threshold) act[p] = t0;
+// order-preserving map double -> uint64 (so that atomicMin/atomicMax on integers order like the doubles)
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// Observers after a split step, one launch: point probes (+ their activation times), per-node activation map,
+// min / max of v over the owned nodes.
+__global__ void observers_kernel(int n_probes, const ProbeDev* __restrict__ probes, const double* __restrict__ x,
+                                 double* __restrict__ vals, double* __restrict__ act, int act_enabled, double threshold, double t0,
+                                 int64_t n_owned, double* __restrict__ actmap, double map_threshold, unsigned long long* __restrict__ minmax) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < n_probes) {
+    const ProbeDev pr = probes[tid];
+    double v = 0.0;
+    for (int k = 0; k < pr.n; ++k) v = fma(pr.w[k], x[pr.node[k]], v);
+    vals[tid] = v;
+    if (act_enabled && act[tid] < 0.0 && v > threshold) act[tid] = t0;
+  }
+  if (actmap == nullptr && minmax == nullptr) return;
+  double lo = INFINITY, hi = -INFINITY;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n_owned; i += stride) {
+    const double v = x[i];
+    lo = fmin(lo, v);
+    hi = fmax(hi, v);
+    if (actmap != nullptr && v > map_threshold && actmap[i] < 0.0) actmap[i] = t0;
+  }
+  if (minmax != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo <= hi) {
+      atomicMin(minmax, ordered_bits(lo));
+      atomicMax(minmax + 1, ordered_bits(hi));
+    }
+  }
+}
+
+__global__ void strided_pack_kernel(int64_t count, int64_t offset, int64_t stride, const double* __restrict__ x, double* __restrict__ out) {
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += step) out[k] = x[offset + k * stride];
 }
 
 }  // namespace
@@ -2067,16 +2219,18 @@ static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_
       int64_t span = 0;
       for (auto& q : cls) span = std::max(span, q.second - q.first + 1);
       int lg = 9;
-      while ((1ll << lg) < span + (int64_t)(kRingMinDepth + 1) * kRingTile + 4) ++lg;
+      while ((1ll << lg) < span + (int64_t)(kRingMinDepth + 1) * kRingTile + kRingChunk) ++lg;
+      auto fits = [&](int l) { return cls.size() * ((size_t)8 << l) + kRingTableSmem + (size_t)kRingStages * (kRingStageBytes + 16) + 256 <= 218 * 1024; };
+      while (((1ll << lg) - span - kRingChunk) / kRingTile - 1 < 3 && fits(lg + 1)) ++lg;  // three tiles ahead if they fit
       const size_t bytes = cls.size() * ((size_t)8 << lg);
-      if (bytes + kRingTableSmem + 64 > 200 * 1024) continue;
+      if (bytes + kRingTableSmem + (size_t)kRingStages * (kRingStageBytes + 16) + 256 > 218 * 1024) continue;
       if (!c->ring_ok || bytes < best_bytes) {
         c->ring_ok = true;
         best_bytes = bytes;
         c->ring_ncl = (int)cls.size();
         c->ring_cap_log2 = lg;
         // the power of two usually leaves room for more tiles in flight than the minimum
-        c->ring_depth = (int)std::min<int64_t>(kRingMaxDepth, ((1ll << lg) - span - 4) / kRingTile - 1);
+        c->ring_depth = (int)std::min<int64_t>(kRingMaxDepth, ((1ll << lg) - span - kRingChunk) / kRingTile - 1);
         for (size_t q = 0; q < cls.size(); ++q) {
           c->ring_lo[q] = cls[q].first;
           c->ring_hi[q] = cls[q].second;
@@ -2131,7 +2285,11 @@ static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_
     MONO_CUDA(c, cudaMemcpyAsync(c->nd_src_dev, nsrc.data(), m * kChunk * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     MONO_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  MONO_CUDA(c, cudaMalloc(&c->pat_dev, (size_t)n));
+  MONO_CUDA(c, cudaMalloc(&c->pat_dev, (size_t)n + 2 * kRingTile));  // (padded: the ring kernel copies whole tiles)
+  MONO_CUDA(c, cudaMemsetAsync(c->pat_dev, 0xff, (size_t)n + 2 * kRingTile, c->stream));
+  MONO_CUDA(c, cudaMalloc(&c->dict_rep_dev, krep.size() * sizeof(int64_t)));
+  MONO_CUDA(c, cudaMalloc(&c->dict_dinv_dev, krep.size() * sizeof(double)));
+  MONO_CUDA(c, cudaMemcpyAsync(c->dict_rep_dev, krep.data(), krep.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
   MONO_CUDA(c, cudaMalloc(&c->dict_off_dev, off.size() * sizeof(int32_t)));
   MONO_CUDA(c, cudaMalloc(&c->dict_cl_dev, cl.size() * sizeof(int32_t)));
   MONO_CUDA(c, cudaMalloc(&c->dict_w_dev, w.size() * sizeof(int32_t)));
@@ -2193,6 +2351,8 @@ int pde_build_sell(mono_ctx* c, const int64_t* indptr, const int32_t* indices, c
   c->max_width = 0;
   for (int64_t s = 0; s < ns; ++s) c->max_width = std::max<int>(c->max_width, (int)((sp[s + 1] - sp[s]) / kSlice));
   MONO_CUDA(c, cudaMalloc(&c->slice_ptr, (ns + 1) * sizeof(int64_t)));
+  MONO_CUDA(c, cudaMalloc(&c->slice_stim_dev, (size_t)ns + 64));
+  MONO_CUDA(c, cudaMemsetAsync(c->slice_stim_dev, 0, (size_t)ns + 64, c->stream));
   MONO_CUDA(c, cudaMalloc(&c->cols, std::max<int64_t>(tot, 1) * sizeof(int32_t)));
   for (double** p : {&c->mass, &c->stiff, &c->A, &c->B}) MONO_CUDA(c, cudaMalloc(p, std::max<int64_t>(tot, 1) * sizeof(double)));
   MONO_CUDA(c, cudaMemcpyAsync(c->slice_ptr, sp.data(), (ns + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
@@ -2224,6 +2384,8 @@ int pde_update_matrices(mono_ctx* c, double dt) {
     c->launches++;
     if (c->n_pat > 0) {
       dict_gather_kernel<<<1, 1024, 0, c->stream>>>(c->n_pat * kChunk, c->dict_src_dev, c->A, c->B, c->dict_A_dev, c->dict_B_dev);
+      c->launches++;
+      dict_dinv_kernel<<<1, 64, 0, c->stream>>>(c->n_pat, c->dict_rep_dev, c->dinv, c->dict_dinv_dev);  // (after jacobi_kernel)
       c->launches++;
       if (c->nd_src_dev != nullptr && c->n_nd > 0) {
         const int64_t m = c->n_nd * kChunk;
@@ -2326,7 +2488,8 @@ static const void* pde_kernel_tbl(bool pipe, bool cheb, bool resident, bool mats
 }
 
 static size_t pde_ring_smem(const mono_ctx* c) {
-  return ((size_t)(kRingTableSmem + 127) / 128) * 128 + ((size_t)c->ring_ncl << c->ring_cap_log2) * 8 + kRingStages * 8 + 64;
+  return ((size_t)(kRingTableSmem + 127) / 128) * 128 + ((size_t)c->ring_ncl << c->ring_cap_log2) * 8 + 2 * kRingStages * 8 +
+         (size_t)kRingStages * kRingStageBytes + 64;
 }
 
 static const void* pde_kernel_for_mode(const mono_ctx* c, bool resident, bool matsmem, bool multi) {
@@ -2386,7 +2549,8 @@ static int pde_select_mode(mono_ctx* c) {
       c->dict_active = false;
     }
     if (c->ring_active) {  // side rows of each CTA's run of slices (same split as the kernel's)
-      const int64_t per_cta = (c->n_slices + c->pde_workers - 1) / c->pde_workers;
+      int64_t per_cta = (c->n_slices + c->pde_workers - 1) / c->pde_workers;
+      per_cta = (per_cta + kRingTile / kSlice - 1) / (kRingTile / kSlice) * (kRingTile / kSlice);
       std::vector<int64_t> ptr((size_t)c->pde_workers + 1, 0);
       for (int b = 0; b <= c->pde_workers; ++b) {
         const int64_t row_lo = std::min<int64_t>((int64_t)b * per_cta, c->n_slices) * kSlice;
@@ -2444,9 +2608,10 @@ static int stim_refresh(mono_ctx* c, double t_eval, int* has_stim) {
       MONO_CUDA(c, cudaMemsetAsync(c->stim_vec, 0, sizeof(double) * nl, c->stream));
     }
     const int threads = 256;
+    MONO_CUDA(c, cudaMemsetAsync(c->slice_stim_dev, 0, (size_t)c->n_slices + 64, c->stream));
     auto launch = [&](const StimDev& st, double scale) {
       const int blocks = (int)std::min<int64_t>((st.nnz + threads - 1) / threads, (int64_t)c->n_sm * 8);
-      stim_scatter_kernel<<<blocks, threads, 0, c->stream>>>(st.nnz, st.idx, st.val, scale, c->stim_vec);
+      stim_scatter_kernel<<<blocks, threads, 0, c->stream>>>(st.nnz, st.idx, st.val, scale, c->stim_vec, c->slice_stim_dev);
       c->launches++;
     };
     for (auto& kv : c->stim_sig) launch(c->stims_host[kv.first], 0.0);
@@ -2534,6 +2699,10 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
   a.nd_A = c->nd_A_dev;
   a.nd_B = c->nd_B_dev;
   a.nd_cta_ptr = c->nd_cta_ptr_dev;
+  a.dict_dinv = c->dict_dinv_dev;
+  a.slice_stim = c->slice_stim_dev;
+  a.dbg = 0;
+  if (const char* e = getenv("MONO_RING_DBG")) a.dbg = atoi(e);
   const bool multi = c->nranks > 1;
   if (multi && !c->peers_ready)
     return mono_fail(c, MONO_E_INVALID, "multi-rank context: call mono_set_halo (on every rank) before stepping the PDE stage");
@@ -2619,8 +2788,9 @@ int pde_build_send_table(mono_ctx* c, const std::vector<int32_t>& row, const std
 
 int probes_launch(mono_ctx* c, double t0) {
   const int n = (int)c->probes_host.size();
-  if (n == 0) return MONO_OK;
-  if (c->probes_dirty) {
+  const bool field = c->actmap_enabled || c->minmax_enabled;
+  if (n == 0 && !field) return MONO_OK;
+  if (n > 0 && c->probes_dirty) {
     if (c->probes_dev) cudaFree(c->probes_dev);
     if (c->probe_vals_dev) cudaFree(c->probe_vals_dev);
     double* old_act = c->probe_act_dev;
@@ -2634,8 +2804,26 @@ int probes_launch(mono_ctx* c, double t0) {
     if (old_act) cudaFree(old_act);
     c->probes_dirty = false;
   }
-  probes_kernel<<<(n + 63) / 64, 64, 0, c->stream>>>(n, c->probes_dev, c->x, c->probe_vals_dev, c->probe_act_dev,
-                                                   c->act_enabled ? 1 : 0, c->act_threshold, t0);
+  int blocks = (n + 255) / 256;
+  if (field) {
+    blocks = std::max(blocks, (int)std::min<int64_t>((c->n_owned + 255) / 256, (int64_t)c->n_sm * 8));
+    if (c->minmax_enabled) {  // identities of min / max in the ordered-integer image
+      const unsigned long long init[2] = {~0ull, 0ull};
+      MONO_CUDA(c, cudaMemcpyAsync(c->minmax_dev, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    }
+  }
+  observers_kernel<<<std::max(blocks, 1), 256, 0, c->stream>>>(n, c->probes_dev, c->x, c->probe_vals_dev, c->probe_act_dev,
+                                                             c->act_enabled ? 1 : 0, c->act_threshold, t0, c->n_owned,
+                                                             c->actmap_enabled ? c->actmap_dev : nullptr, c->actmap_threshold,
+                                                             c->minmax_enabled ? c->minmax_dev : nullptr);
+  c->launches++;
+  MONO_CUDA(c, cudaGetLastError());
+  return MONO_OK;
+}
+
+int strided_pack_launch(mono_ctx* c, int64_t offset, int64_t stride, int64_t count, double* out_dev) {
+  const int blocks = (int)std::min<int64_t>((count + 255) / 256, (int64_t)c->n_sm * 8);
+  strided_pack_kernel<<<std::max(blocks, 1), 256, 0, c->stream>>>(count, offset, stride, c->x, out_dev);
   c->launches++;
   MONO_CUDA(c, cudaGetLastError());
   return MONO_OK;

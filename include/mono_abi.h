@@ -200,6 +200,17 @@ int mono_probe_values(mono_ctx *ctx, double *values); /* current value of every 
  * (niederer_benchmark.py:284-287); -1 while not activated.                                         */
 int mono_probe_activation(mono_ctx *ctx, double threshold);
 int mono_probe_activation_times(mono_ctx *ctx, double *times);
+/* Whole-field observers evaluated on the device after every split step, in the same launch as the probes, so that a
+ * run never has to copy V to the host to follow it (what the demos do with state.x.array every step:
+ * demos/niederer_benchmark.py:271-287 logs v.max()/v.min() and compares point values with 0, README.md:197-201):
+ *   activation map: for every OWNED node the start time t0 of the first split step after which v > threshold, -1 before;
+ *   min/max:        extrema of v over the owned nodes after the last split step.                                  */
+int mono_observe_config(mono_ctx *ctx, int activation_map, double threshold, int minmax);
+int mono_activation_map(mono_ctx *ctx, double *times_owned);            /* n_owned values; synchronises */
+int mono_v_minmax(mono_ctx *ctx, double *vmin, double *vmax);           /* of the last split step; synchronises */
+/* Strided snapshot: out[k] = v[offset + k*stride], k < count (gathered on the device, one small copy: frames for
+ * plotting / coarse output without moving the whole field).                                                   */
+int mono_get_v_strided(mono_ctx *ctx, int64_t offset, int64_t stride, int64_t count, double *out);
 
 /* ---- host-side set-up helper (no GPU involved) -------------------------------------------------- */
 /* P1 simplex assembly of the OWNED rows (0..n_owned-1) of the mass matrix  v*w*dx  and the stiffness matrix

@@ -166,6 +166,60 @@ def test_niederer_api_matches_oracle_and_probes():
     assert np.allclose(solver.pde.probe_values()[info["probe_ids"]["P1"]], v[0])
 
 
+def test_random_activation_through_the_model():
+    """stimulation.generate_random_activation (src/beat/stimulation.py:279-363) as I_s of the PDE model with M = 0: the
+    charge int v dx grows by dt * amplitude * |marked cells| for every step whose theta-point lies in a point's window."""
+    beat = _beat()
+    fem = beat.fem
+    mesh = fem.create_box(fem.COMM_SELF, [np.zeros(3), np.ones(3)], [4, 4, 4])
+    time = fem.Constant(mesh, 0.0)
+    points, delays = np.array([[0.5, 0.5, 0.5], [1.0, 1.0, 1.0]]), np.array([1.0, 3.0])
+    I_s = beat.stimulation.generate_random_activation(mesh=mesh, time=time, points=points, delays=delays, stim_start=0.0,
+                                                      stim_duration=1.0, stim_amplitude=5.0, tol=0.2)
+    pde = beat.MonodomainModel(time=time, mesh=mesh, M=0.0, I_s=I_s, params={"theta": 0.5})
+    cent = mesh.geometry.x[mesh.cells].mean(axis=1).T
+    vol = [float((term.g(cent) > 0).sum()) / (64 * 6) for term in I_s.terms]
+    ones = fem.load_vector(mesh, fem.dx(domain=mesh), None)  # Mass * 1
+    dt, t, want = 0.1, 0.0, 0.0
+    for _ in range(50):
+        pde.step((t, t + dt))
+        pde.assign_previous()
+        tm = t + 0.5 * dt
+        for term, vo in zip(I_s.terms, vol):
+            if term.start <= tm <= term.end:
+                want += dt * 5.0 * vo
+        t += dt
+        assert abs(float(ones @ pde.state.x.array_ro) - want) <= 1e-9 * max(want, 1.0)
+    assert want > 0
+
+
+def test_whole_field_observers_match_host_tracking():
+    """the per-node activation map, min / max of v and a strided snapshot computed on the device equal what the
+    demos compute from state.x.array on the host after every step (demos/niederer_benchmark.py:271-287)."""
+    from beat_b200 import niederer
+
+    solver, info = niederer.setup(dx=0.5, rtol=1e-10)
+    pde = solver.pde
+    pde.observe(activation_map=True, threshold=0.0, minmax=True)
+    n = info["n_owned"]
+    act = np.full(n, -1.0)
+    dt, t = 0.05, 0.0
+    for k in range(80):
+        solver.step((t, t + dt))
+        v = np.array(pde.state.x.array_ro)[:n]
+        newly = (v > 0.0) & (act < 0.0)
+        act[newly] = t
+        if k % 20 == 19:
+            lo, hi = pde.v_minmax()
+            assert lo == v.min() and hi == v.max()
+        t += dt
+    got = pde.activation_map()
+    assert (act >= 0).sum() > 10 and (act < 0).sum() > 10  # the front is somewhere inside the slab
+    assert np.array_equal(got, act)
+    assert np.array_equal(pde.state_snapshot(stride=7, offset=3), v[3::7])
+    assert np.array_equal(pde.state_snapshot(stride=1), v)
+
+
 def test_ode_system_solver():
     """src/beat/odesolver.py:46-79: the plain driver, states held by reference, shared and per-node parameters."""
     beat = _beat()

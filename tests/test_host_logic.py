@@ -99,6 +99,34 @@ def test_define_stimulus_units_and_window():  # tests/test_stimulation.py:253-30
     assert stim.expr.amplitude_now() == 7.0
 
 
+def test_generate_random_activation():  # tests/test_stimulation.py:305-380 of the reference, evaluated at the cell centroids (DG0)
+    mesh = fem.create_box(fem.COMM_SELF, [np.zeros(3), np.ones(3)], [4, 4, 4])
+    t = fem.Constant(mesh, 0.0)
+    points = np.array([[0.5, 0.5, 0.5], [1.0, 1.0, 1.0]])
+    expr = stimulation.generate_random_activation(mesh=mesh, time=t, points=points, delays=np.array([1.0, 3.0]), stim_start=0.0,
+                                                  stim_duration=1.0, stim_amplitude=5.0, tol=0.2)
+    cent = mesh.geometry.x[mesh.cells].mean(axis=1).T
+
+    def at(tv):
+        t.value = tv
+        return expr.evaluate(cent)
+
+    assert np.allclose(at(0.5), 0.0)
+    assert at(1.5).max() == pytest.approx(5.0) and at(1.5).min() == pytest.approx(0.0)
+    assert np.allclose(at(2.5), 0.0)
+    assert at(3.5).max() == pytest.approx(5.0)
+    assert np.allclose(at(4.5), 0.0)
+    first = expr.terms[0]
+    assert (first.start, first.end) == (1.0, 2.0)
+    # its load vector: int 1[x near p] phi_i dx with the centroid rule = (volume of the marked cells) / 4 per vertex
+    load = fem.load_vector(mesh, fem.dx(domain=mesh), None, first.g, first.degree)
+    marked = first.g(cent) > 0
+    assert marked.sum() > 0 and np.isclose(load.sum(), marked.sum() * (1.0 / 64) / 6)
+    with pytest.raises(AssertionError):
+        stimulation.generate_random_activation(mesh=mesh, time=t, points=np.zeros((2, 3)), delays=np.zeros(3))
+    assert len(stimulation.generate_random_activation(mesh=mesh, time=t, points=np.zeros((0, 3)), delays=np.zeros(0)).terms) == 0
+
+
 def test_conductivities():  # src/beat/conductivities.py:29-118
     c = conductivities.default_conductivities("Niederer")
     s_l, s_t = conductivities.get_harmonic_mean_conductivity(**c)

@@ -20,6 +20,13 @@ CASES = [
     dict(dx=0.125, dt=0.05, nsteps=4, theta=1.0, ksp="pipecg", x0_prev=False, rtol=1e-11, tol=1e-8),  # several rows per thread
     dict(dx=0.5, dt=0.05, nsteps=6, theta=1.0, ksp="cg", x0_prev=False, rtol=1e-12, tol=1e-8, env={"MONO_PDE_STREAM": "1"}),
     dict(dx=0.25, dt=0.05, nsteps=4, theta=1.0, ksp="pipecg", x0_prev=False, rtol=1e-11, tol=1e-8, env={"MONO_PDE_STREAM": "1"}),
+    # streaming KSPCG in its other modes: dictionary through the L1 (no rings), SELL stream (no dictionary), x0 = v_ with the
+    # rings, the tagged-exchange kernel; and a finer mesh with several ring tiles per CTA
+    dict(dx=0.5, dt=0.05, nsteps=6, theta=1.0, ksp="cg", x0_prev=False, rtol=1e-12, tol=1e-8, env={"MONO_PDE_STREAM": "1", "MONO_PDE_NO_RING": "1"}),
+    dict(dx=0.5, dt=0.05, nsteps=6, theta=1.0, ksp="cg", x0_prev=False, rtol=1e-12, tol=1e-8, env={"MONO_PDE_STREAM": "1", "MONO_PDE_DICT": "0"}),
+    dict(dx=0.5, dt=0.05, nsteps=6, theta=0.5, ksp="cg", x0_prev=True, rtol=1e-12, tol=1e-8, env={"MONO_PDE_STREAM": "1"}),
+    dict(dx=0.5, dt=0.05, nsteps=6, theta=1.0, ksp="cg", x0_prev=False, rtol=1e-12, tol=1e-8, env={"MONO_PDE_STREAM": "1", "MONO_PDE_TAGGED_STREAM": "1"}),
+    dict(dx=0.125, dt=0.05, nsteps=4, theta=1.0, ksp="cg", x0_prev=False, rtol=1e-12, tol=1e-8, env={"MONO_PDE_STREAM": "1"}),
     dict(dx=0.5, dt=0.05, nsteps=12, theta=1.0, ksp="pipecg", pc="chebyshev", x0_prev=False, rtol=1e-11, tol=1e-8),
     dict(dx=0.25, dt=0.05, nsteps=6, theta=0.5, ksp="pipecg", pc="chebyshev", x0_prev=True, rtol=1e-11, tol=1e-8),
     dict(dx=0.0, lv=[3, 12, 32], dt=0.05, nsteps=12, theta=1.0, ksp="pipecg", x0_prev=False, rtol=1e-11, tol=1e-8),

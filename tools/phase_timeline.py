@@ -15,6 +15,8 @@ t, dt = 0.0, 0.01
 for _ in range(10):
     solver.step((t, t + dt)); t += dt
 ctx.debug_timeline(True, False)
+if os.environ.get("TIMELINE_DBG"):  # ablation switches of the ring kernel, applied to the measured launches only
+    os.environ["MONO_RING_DBG"] = os.environ["TIMELINE_DBG"]
 for rep in range(2):
     ctx.split_step(t, t + dt, 1.0); t += dt
     st = np.array(ctx.debug_timeline(True, True), dtype=np.int64)

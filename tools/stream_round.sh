@@ -1,11 +1,13 @@
 #!/bin/bash
-# Streaming KSPCG kernel (plain vectors + fenced barrier) against the tagged one on the streaming sizes (1 GPU).
+# Streaming KSPCG kernel variants on the streaming sizes (1 GPU): rings (default), dictionary through the L1, tagged exchange.
 # usage: bash tools/stream_round.sh TAG [workloads...]
 T=${1:-r02s}; shift; O=gpurun_out; mkdir -p $O
 WL=${@:-"niederer_dx0.05 niederer_dx0.025"}
 for w in $WL; do
-  for mode in plain tagged; do
-    [ $mode = tagged ] && export MONO_PDE_TAGGED_STREAM=1 || unset MONO_PDE_TAGGED_STREAM
+  for mode in ring l1 tagged; do
+    unset MONO_PDE_TAGGED_STREAM MONO_PDE_NO_RING
+    [ $mode = tagged ] && export MONO_PDE_TAGGED_STREAM=1
+    [ $mode = l1 ] && export MONO_PDE_NO_RING=1
     timeout 900 python bench.py --workload $w --secondary none --steps 20 --warmup 5 --no-cpu-baseline --no-extras \
       > $O/${T}_bench_${w}_$mode.json 2> $O/${T}_bench_${w}_$mode.err
     python - <<PY
@@ -18,4 +20,4 @@ except Exception as e:
 PY
   done
 done
-unset MONO_PDE_TAGGED_STREAM
+unset MONO_PDE_TAGGED_STREAM MONO_PDE_NO_RING

@@ -65,7 +65,7 @@ def test_lexicographic_order_restores_the_dictionary_on_reordered_dofs():
     As.data, Ks.data = mass[order], stiff[order]
     xs = mesh.geometry.x[scr]
     pat, rep, cnt = csr_row_patterns(As.indptr, As.indices, As.data, Ks.data)
-    assert cnt.sum() < 0.2 * n  # scrambled: (almost) no two rows share their column offsets
+    assert cnt.max() <= 2  # scrambled: (almost) no two rows share their column offsets
     perm, shape = da.lexicographic_order(xs)
     assert shape == (9, 7, 5)
     ip, ix, (m2, k2) = da.permute_csr(As.indptr, As.indices, [As.data, Ks.data], perm, n)

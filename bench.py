@@ -425,25 +425,33 @@ def measure(D: Dist, args, workload: str, scaling: str, K: int, W: int, full: bo
     e2e = None
     ode, pde = solver.ode, solver.pde
     if full:
+        import torch
+
         npts = int(ode.v_ode.x.array_ro.size)  # owned + ghost dofs (num_points is a per-marker method on the multi-region solver)
-        host_v = np.array(pde.state.x.array_ro)  # D2H
+        torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // max(1, world))))  # (torchrun pins OMP to 1 thread)
         ke = min(K, 500)
+        t_out, t_in = torch.from_numpy(pde.state.x.array), torch.from_numpy(ode.v_ode.x.array)  # views of the two page-locked mirrors
+        solver.step((t, t + dt))  # (the writable views above marked both mirrors host-dirty: settle that outside the timed region)
+        t += dt
         barrier()
         t_e0 = time.perf_counter()
         ctx.event_record(2 * K + 2)
         for k in range(ke):
-            ode.v_ode.x.array[:] = host_v            # host owns V: written into the pinned mirror ...
+            out = pde.state.x.array_ro               # D2H of the result into its page-locked mirror (what the demos read every step)
+            vin = ode.v_ode.x.array_wo               # the host OWNS V between steps: it writes the whole page-locked input mirror ...
+            t_in.copy_(t_out)                        # (... here: the V it just read; torch's multi-threaded host copy of vin[:] = out)
             ode.from_dolfin()                        # ... H2D + states[v_index] <- v_ode (odesolver.py:168-170)
             solver.step((t, t + dt))
-            host_v[:] = pde.state.x.array_ro         # D2H of the result the demos read every step
             t += dt
+        out = pde.state.x.array_ro                   # the last result
         ctx.event_record(2 * K + 3)
         barrier()
         e2e_wall_ms = (time.perf_counter() - t_e0) * 1e3
         e2e_ms = D.max(max(ctx.event_elapsed_ms(2 * K + 2, 2 * K + 3), e2e_wall_ms))
         e2e = {"value": n_global * ke / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * npts,
                "d2h_bytes_per_step": 8 * npts, "steps": ke, "ms_per_step": e2e_ms / ke,
-               "path": "v_ode.x.array[:]=host_v; ode.from_dolfin(); solver.step((t,t+dt)); host_v[:]=pde.state.x.array"}
+               "path": "out=pde.state.x.array_ro [D2H]; ode.v_ode.x.array_wo[:]=out [host copy into the pinned input mirror]; "
+                       "ode.from_dolfin() [H2D]; solver.step((t,t+dt))"}
     clk = clocks.stop() if clocks else None
     check = selfcheck(D, solver, ctx, n_owned)
 

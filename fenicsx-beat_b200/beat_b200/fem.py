@@ -922,6 +922,16 @@ class Vector:
         return self._host
 
     @property
+    def array_wo(self) -> np.ndarray:
+        """The host array for a caller that OVERWRITES all of it: no download of the device copy first (``.array`` has to
+        assume a partial update and refreshes the mirror before handing it out); the next device operation uploads it."""
+        self._upload_guard()
+        self.device_newer = False
+        if self._upload is not None:
+            self.host_dirty = True
+        return self._host
+
+    @property
     def array_ro(self) -> np.ndarray:
         self._pull()
         v = self._host.view()

@@ -2154,6 +2154,9 @@ static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_
   int64_t covered = 0;
   for (int p = 0; p < npat; ++p) {
     if (indptr[rep[p] + 1] - indptr[rep[p]] > kChunk) continue;
+    bool ghost = false;  // a stencil that reaches into the ghost block (row next to a partition cut) is not a dictionary stencil
+    for (int64_t k = indptr[rep[p]]; k < indptr[rep[p] + 1]; ++k) ghost |= indices[k] >= n;
+    if (ghost) continue;
     remap[p] = (int)krep.size();
     krep.push_back(rep[p]);
     covered += cnt[p];
@@ -2175,9 +2178,6 @@ static int pde_build_dictionary(mono_ctx* c, const int64_t* indptr, const int32_
         }
     pat[(size_t)r] = q;
   }
-  for (int64_t r : krep)
-    for (int64_t k = indptr[r]; k < indptr[r + 1]; ++k)
-      if (indices[k] >= n) covered = 0;  // (a stencil whose representative reaches into the ghosts: no such mesh generator here)
   c->dict_cover = (double)covered / (double)n;
   if (c->dict_cover < 0.5) {
     c->n_pat = 0;

@@ -69,6 +69,11 @@ def main(argv=None) -> int:
     setup_s = time.perf_counter() - t_setup
 
     def merged_times() -> np.ndarray:
+        # EVERY rank drains its own stream before the torch collective below: a rank without probes would otherwise launch
+        # the NCCL kernel while its persistent PDE kernels (cooperative, one CTA with all registers per SM) are still queued
+        # behind it - they cannot become resident next to the NCCL CTAs, NCCL waits for the peers, the peers wait in
+        # cudaStreamSynchronize for kernels that wait for this rank: a deadlock (seen on 8 GPUs, r02n).
+        ctx.sync()
         local = np.full(len(names), -1.0)
         if mine:
             act = solver.pde.activation_times()

@@ -26,6 +26,14 @@ def test_activation_times_dx05_dt005_within_one_dt():
     assert np.abs(d).max() <= 0.05 + 1e-9, d
 
 
+def test_activation_times_dx02_dt005_within_one_dt():
+    """The second published resolution (dx = 0.2, 58 176 nodes - the mesh of BASELINE config 2 - at dt = 0.05): every point
+    within one dt of niederer_benchmark.py:320 (got 1.30 29.75 32.85 40.15 9.55 30.05 32.90 39.90 18.90)."""
+    act = N.run(0.2, 0.05, T=45.0, tp06=P.oracle_model("tp06"))
+    d = np.array([act[k] for k in N.POINTS]) - np.array(N.PUBLISHED[(0.2, 0.05)])
+    assert np.abs(d).max() <= 0.05 + 1e-9, d
+
+
 def test_activation_times_dx05_dt001():
     d = _diff(0.5, 0.01, rtol=1e-10)
     assert np.abs(d).max() <= 0.06, d  # ms: 0.1 % of the arrival times; solver-tolerance residual of the reference

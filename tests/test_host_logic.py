@@ -329,3 +329,44 @@ def test_vector_mirror_coherence_protocol():
     a.mark_device_newer()                                # a changed again: b must fetch its own content
     log.clear()
     assert b.array_ro.tolist() == [2, 2, 2, 2] and log == [("down", "b")]
+
+
+def test_vector_write_only_access_skips_the_download():
+    """fem.Vector.array_wo: for a caller that overwrites the whole array (bench.py's e2e loop: the host owns V between
+    steps) - no device-to-host transfer first, the content is uploaded by the next device operation, and an upload still
+    in flight is waited for before the buffer is handed out."""
+    log = []
+    dev = {"a": np.full(4, 5.0)}
+    a = fem.Vector(4)
+    a.bind(lambda out: (log.append("down"), out.__setitem__(slice(None), dev["a"])), lambda src: (log.append("up"), dev.__setitem__("a", np.array(src))),
+           push_now=False, sync=lambda: log.append("sync"))
+    a.mark_device_newer()
+    w = a.array_wo
+    assert log == [] and not a.device_newer and a.host_dirty     # nothing fetched; the host copy is now the truth
+    w[:] = [1.0, 2.0, 3.0, 4.0]
+    a.flush_to_device()
+    assert log == ["up"] and dev["a"].tolist() == [1, 2, 3, 4]
+    _ = a.array_wo                                                # asynchronous upload: wait before exposing the buffer again
+    assert log == ["up", "sync"]
+    a.mark_device_newer()
+    assert a.array.tolist() == [1, 2, 3, 4] and log[-1] == "down"  # the ordinary accessor still fetches
+
+
+def test_bench_workload_description_is_the_same_in_both_arms():
+    """bench.py: the `config` object depends only on (workload, scaling, world) - the driver compares the two arms' configs -
+    and the CPU arm's sample is a bounded x-block of the same slab."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    c1 = bench.workload_config("niederer_dx0.025", "strong", 8)
+    assert c1 == bench.workload_config("niederer_dx0.025", "strong", 8) and c1["nodes"] == 801 * 281 * 121 and "model" not in c1
+    assert bench.workload_config("niederer_dx0.2", "weak", 2)["nodes"] == 201 * 36 * 16
+    assert bench.slab_nodes(0.2, 20.0) == 58176
+    for dx in (0.5, 0.2, 0.1, 0.05, 0.025, 0.016):
+        L = bench.cpu_sample_length(dx)
+        assert 0 < L <= 20.0 and bench.slab_nodes(dx, L) <= 2.0e6
+        assert abs(L / dx - round(L / dx)) < 1e-9                 # a whole number of elements
+    assert bench.cpu_sample_length(0.2) == 20.0                   # small slabs are timed whole
+    assert bench.cpu_sample_length(0.025) >= 1.25 - 1e-9          # ... large ones on a block of >= 16 elements incl. the stimulus corner

@@ -19,6 +19,12 @@ MODEL_ID = {"fhn": 0, "tp06": 1, "torord": 2}
 VNAME = {"fhn": "v", "tp06": "V", "torord": "v"}
 
 
+# what ties the cell model's arithmetic to the reference
+PIN = {"tp06": "published Niederer activation times (demos/niederer_benchmark.py:315-325) through the oracle",
+       "fhn": "README.md:58-89 closed form (forward Euler); GRL1: device <-> oracle only",
+       "torord": "UNPINNED: no reference test or demo output exercises ToR-ORd; device <-> oracle only"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--models", default="tp06,torord")
@@ -84,7 +90,8 @@ def main():
                 print(json.dumps({"workload": f"ode_only {tag} {args.scheme}", "n_gpus": world, "nodes": n_total, "ms_per_step": ms,
                                   "node_steps_per_s": n_total / (ms * 1e-3), "per_gpu": {"fp64_tflops_equiv": flops, "dfma_peak_tflops": dfma,
                                   "fp64_frac": flops / dfma, "state_gbs": gbs, "hbm_frac": gbs / hbm}, "fp64_instr_per_node": instr,
-                                  "finite": bool(np.isfinite(v).all()), "variant": os.environ.get("MONO_ODE_VARIANT", "auto")}), flush=True)
+                                  "finite": bool(np.isfinite(v).all()), "variant": os.environ.get("MONO_ODE_VARIANT", "auto"),
+                                  "reference_pin": PIN[tag]}), flush=True)
             ctx.close()
     if dist is not None:
         dist.barrier()

@@ -20,12 +20,12 @@ PY
 }
 nvidia-smi -L | wc -l
 timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q -k "$NG" > $O/${T}_mgpu_pytest.log 2>&1; tail -3 $O/${T}_mgpu_pytest.log
-for n in 1 2 4 8; do [ $n -le $NG ] && run $n weak_dx0.2_n$n --steps 300 --warmup 10 --no-cpu-baseline; done
+for n in 1 2 4 8; do [ $n -le $NG ] && run $n weak_dx0.2_n$n --workload niederer_dx0.2 --scaling weak --secondary none --steps 300 --warmup 10 --no-cpu-baseline; done
 STRONG_N=${STRONG_N:-"1 2 4 8"}
-for n in $STRONG_N; do [ $n -le $NG ] && run $n strong_dx0.05_n$n --workload niederer_dx0.05 --scaling strong --steps 30 --warmup 5 --no-cpu-baseline --no-extras; done
-for n in $STRONG_N; do [ $n -le $NG ] && [ $n -gt 1 ] && run $n strong_dx0.025_n$n --workload niederer_dx0.025 --scaling strong --steps 20 --warmup 5 --no-cpu-baseline --no-extras; done
-for n in 1 8; do [ $n -le $NG ] && run $n weak_lv320k_n$n --workload lv_ellipsoid_320k --steps 100 --warmup 5 --no-cpu-baseline --no-extras; done
-for n in 1 8; do [ $n -le $NG ] && run $n strong_lv1.4M_n$n --workload lv_ellipsoid_1.4M --scaling strong --steps 50 --warmup 5 --no-cpu-baseline --no-extras; done
+for n in $STRONG_N; do [ $n -le $NG ] && run $n strong_dx0.05_n$n --workload niederer_dx0.05 --scaling strong --secondary none --steps 30 --warmup 5 --no-cpu-baseline --no-extras; done
+for n in $STRONG_N; do [ $n -le $NG ] && [ $n -gt 1 ] && run $n strong_dx0.025_n$n --workload niederer_dx0.025 --scaling strong --secondary none --steps 20 --warmup 5 --no-cpu-baseline --no-extras; done
+for n in 1 8; do [ $n -le $NG ] && run $n weak_lv320k_n$n --workload lv_ellipsoid_320k --scaling weak --secondary none --steps 100 --warmup 5 --no-cpu-baseline --no-extras; done
+for n in 1 8; do [ $n -le $NG ] && run $n strong_lv1.4M_n$n --workload lv_ellipsoid_1.4M --scaling strong --secondary none --steps 50 --warmup 5 --no-cpu-baseline --no-extras; done
 # BASELINE config 3 on all GPUs: ODE-only, nodes split over the ranks
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29877 tools/ode_sweep.py \
   --models tp06,torord --nodes 1e8 --steps 20 > $O/${T}_ode_sweep_n$NG.jsonl 2> $O/${T}_ode_sweep_n$NG.err; cut -c1-220 $O/${T}_ode_sweep_n$NG.jsonl

@@ -73,3 +73,63 @@ def test_lexicographic_order_restores_the_dictionary_on_reordered_dofs():
     pat2, rep2, cnt2 = csr_row_patterns(ip, ix, m2, k2)
     assert cnt2.sum() == n and len(cnt2) == 27  # every row is one of the 27 box stencils again
     assert da.lexicographic_order(xs[:-1]) is None  # not a full grid
+
+
+# ---- the collective half: index_map_arrays over real processes (gloo), with an mpi4py-shaped communicator -------------
+def _adapter_worker(rank, world, store_path, result_path):
+    """An interval mesh: its x-partition owns CONTIGUOUS global ranges, as dolfinx IndexMaps do (the adapter turns a global
+    index into a local one with `global - local_range[0]`)."""
+    import sys as _sys
+
+    for p in (ROOT, os.path.join(ROOT, "fenicsx-beat_b200")):
+        if p not in _sys.path:
+            _sys.path.insert(0, p)
+    import torch.distributed as dist
+
+    from beat_b200 import dolfinx_adapter as da2
+    from beat_b200 import fem as fem2
+
+    dist.init_process_group("gloo", init_method=f"file://{store_path}", rank=rank, world_size=world)
+
+    class Comm:  # the mpi4py surface the adapter uses
+        size = world
+
+        def __init__(self):
+            self.rank = rank
+
+        def alltoall(self, send):  # (gloo has no object all-to-all: gather every rank's row, pick our column)
+            table = [None] * world
+            dist.all_gather_object(table, [np.asarray(s) for s in send])
+            return [table[q][rank] for q in range(world)]
+
+    mesh = fem2.create_interval(fem2.Comm(rank, world), 17)
+    im = mesh.index_map
+    owned_g = im.local_to_global[: im.size_local]
+    assert np.array_equal(owned_g, np.arange(owned_g[0], owned_g[0] + im.size_local))
+    shuffle = np.random.default_rng(100 + rank).permutation(im.num_ghosts)  # dolfinx promises no ghost order
+
+    class IMap:  # the dolfinx IndexMap attributes the adapter reads
+        ghosts, owners = im.ghosts[shuffle], im.owners[shuffle]
+        size_local = im.size_local
+        local_range = (int(owned_g[0]), int(owned_g[-1]) + 1)
+
+    perm, nbr, send_ptr, send_idx, recv_ptr = da2.index_map_arrays(IMap, Comm())
+    ok = (np.array_equal(IMap.ghosts[perm], im.ghosts) and np.array_equal(nbr, im.nbr_ranks) and np.array_equal(recv_ptr, im.recv_ptr)
+          and np.array_equal(send_ptr, im.send_ptr) and np.array_equal(send_idx, im.send_idx))
+    np.save(f"{result_path}.{rank}.npy", np.array([ok]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_index_map_arrays_over_three_gloo_ranks():
+    """dolfinx_adapter.index_map_arrays (collective) reproduces, from shuffled ghosts and an all-to-all of the wanted global
+    indices, the halo arrays the package's own partitioner builds."""
+    import tempfile
+
+    import torch.multiprocessing as mp
+
+    with tempfile.TemporaryDirectory() as tmp:
+        store, res = os.path.join(tmp, "store"), os.path.join(tmp, "res")
+        mp.spawn(_adapter_worker, args=(3, store, res), nprocs=3, join=True)
+        for rank in range(3):
+            assert bool(np.load(f"{res}.{rank}.npy")[0]), rank

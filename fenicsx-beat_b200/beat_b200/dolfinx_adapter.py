@@ -2,11 +2,11 @@
 `BaseModel._setup` (src/beat/base_model.py:100-128) and `DolfinODESolver.__post_init__` (src/beat/odesolver.py:148-153)
 instead of creating PETSc objects.  INTEGRATION.md walks through the same calls.
 
-STATUS: the functions that touch dolfinx / ufl / mpi4py (`csr_from_forms`, `stimulus_load`, `index_map_arrays`,
-`build_context`) are UNTESTED here - none of those packages can be installed in this environment (SURVEY.md section 0);
-they are written against the dolfinx 0.9 Python API and import it lazily.  The array logic they rely on - grouping ghosts
-by owner, the send lists that mirror the neighbours' ghost blocks, the structured-numbering detection - is plain NumPy, lives
-in the `*_arrays` / `lexicographic_order` functions below and IS tested (tests/test_dolfinx_adapter.py).
+STATUS: the functions that touch dolfinx / ufl (`csr_from_forms`, `stimulus_load`, `build_context`) are UNTESTED here - those
+packages cannot be installed in this environment; they are written against the dolfinx 0.9 Python API
+and import it lazily.  The array logic they rely on - grouping ghosts by owner, the send lists that mirror the neighbours'
+ghost blocks, the structured-numbering detection - is plain NumPy and IS tested (tests/test_dolfinx_adapter.py), and so is
+the collective `index_map_arrays`, over three gloo processes with an mpi4py-shaped communicator and IndexMap stand-in.
 """
 
 from __future__ import annotations

@@ -413,8 +413,9 @@ int mono_pde_set_matrices(mono_ctx* c, int64_t n_owned, int64_t n_ghost, const i
   if (rc) return rc;
   const int64_t nl = std::max<int64_t>(c->n_local, 32);
   for (double** p : {&c->x, &c->v_prev, &c->dinv}) {
-    MONO_CUDA(c, cudaMalloc(p, sizeof(double) * nl));
-    MONO_CUDA(c, cudaMemsetAsync(*p, 0, sizeof(double) * nl, c->stream));
+    // (+2: the ring kernel's bulk copies are 16-byte granular and may read one element past an odd-sized vector)
+    MONO_CUDA(c, cudaMalloc(p, sizeof(double) * (nl + 2)));
+    MONO_CUDA(c, cudaMemsetAsync(*p, 0, sizeof(double) * (nl + 2), c->stream));
   }
   c->has_pde = true;
   rc = pde_setup_launch_config(c);

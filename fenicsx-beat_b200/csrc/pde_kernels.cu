@@ -2636,8 +2636,8 @@ int pde_launch_step(mono_ctx* c, double t_eval, double dt) {
     for (int k = 0; k < 10; ++k) {
       const bool needed = c->stream_plain ? (k == VR || k == VQ || k == VP) : true;  // KSPCG keeps r, q, p (x, d alias a.x, a.dinv)
       if (needed && !c->work[k]) {
-        MONO_CUDA(c, cudaMalloc(&c->work[k], sizeof(double) * no));
-        MONO_CUDA(c, cudaMemsetAsync(c->work[k], 0, sizeof(double) * no, c->stream));
+        MONO_CUDA(c, cudaMalloc(&c->work[k], sizeof(double) * (no + 2)));  // (+2: see mono_pde_set_matrices)
+        MONO_CUDA(c, cudaMemsetAsync(c->work[k], 0, sizeof(double) * (no + 2), c->stream));
       }
     }
   }

@@ -80,6 +80,16 @@ class ODESystemSolver:
             self._ctx.ode_step(t0, dt)
             self._mirror.mark_device_newer()
 
+    def state_row(self, index: int) -> np.ndarray:
+        """One state (e.g. the membrane potential) of all points, without moving the other rows."""
+        self._mirror.flush()
+        return self._ctx.ode_get_state_row(int(index))
+
+    def set_state_row(self, index: int, values: np.ndarray) -> None:
+        self._mirror.flush()
+        self._ctx.ode_set_state_row(int(index), np.ascontiguousarray(values, dtype=np.float64))
+        self._mirror.mark_device_newer()
+
 
 class BaseDolfinODESolver(abc.ABC):
     v_ode: fem.Function
@@ -280,6 +290,17 @@ class DolfinMultiODESolver(DolfinODESolver):
     reference's demos (ToR-ORd / TP06 with endo / mid / epi parameter sets); different models per region raise
     NotImplementedError."""
 
+    def __new__(cls, v_ode=None, v_pde=None, markers=None, init_states=None, parameters=None, fun=None, num_states=None,
+                v_index=None, monitor=None, **kw):
+        # different cell MODELS (or schemes / v_index) per region: one device ODE stage per region (MixedModelODESolver)
+        if cls is DolfinMultiODESolver and isinstance(fun, dict) and isinstance(v_index, dict) and init_states is not None:
+            funs = [fun[m] for m in init_states]
+            if all(isinstance(f, DeviceODE) for f in funs) and (
+                    len({(f.model_id, f.scheme_id) for f in funs}) != 1 or len({v_index[m] for m in init_states}) != 1):
+                return MixedModelODESolver(v_ode=v_ode, v_pde=v_pde, markers=markers, init_states=init_states, parameters=parameters,
+                                           fun=fun, num_states=num_states, v_index=v_index, monitor=monitor, **kw)
+        return super().__new__(cls)
+
     def __init__(self, v_ode: fem.Function, v_pde: fem.Function, markers: fem.Function, init_states: dict, parameters: dict,
                  fun: dict, num_states: dict, v_index: dict, monitor: BaseMonitor | None = None):
         if v_ode.x.array_ro.size != markers.x.array_ro.size:
@@ -289,8 +310,8 @@ class DolfinMultiODESolver(DolfinODESolver):
         if any(not isinstance(f, DeviceODE) for f in funs):
             raise TypeError("fun[marker] must be device model handles (there is no CPU fallback)")
         if len({(f.model_id, f.scheme_id) for f in funs}) != 1 or len({v_index[m] for m in self._marker_values}) != 1:
-            raise NotImplementedError("the device path runs one cell model (and scheme, v_index) over all regions; "
-                                      "regions may differ in parameters and initial states")
+            raise NotImplementedError("one cell model over all regions here; DolfinMultiODESolver(...) dispatches mixed models "
+                                      "to MixedModelODESolver")
         marr = np.asarray(markers.x.array_ro)
         self.markers = markers
         self._inds = {m: marr == m for m in self._marker_values}
@@ -344,3 +365,102 @@ class DolfinMultiODESolver(DolfinODESolver):
     @property
     def full_values(self) -> np.ndarray:
         return self._mirror.get()
+
+
+class MixedModelODESolver(BaseDolfinODESolver):
+    """``DolfinMultiODESolver`` with DIFFERENT cell models per region (src/beat/odesolver.py:228-354 allows any callable per
+    marker; demos/lv_endocardial.py:203-257 uses one model with three parameter sets, which the single-launch
+    DolfinMultiODESolver above serves).  One device ODE stage (``ODESystemSolver``, its own context and compact state array)
+    per region; the membrane potential is exchanged with the PDE stage through the host mirrors of ``v_ode`` / ``v_pde`` -
+    one row per region and direction per hand-off, so this path costs PCIe traffic every step and runs through the
+    splitting solver's protocol sequence (monodomain_solver.py:66-113), not the fused device step.  It exists so that the
+    reference's interface is complete; it is a composition of device primitives that are each covered by the GPU tests and
+    is itself exercised on the CPU with a stand-in for the device stage (tests/test_host_logic.py)."""
+
+    def __init__(self, v_ode: fem.Function, v_pde: fem.Function, markers: fem.Function, init_states: dict, parameters: dict,
+                 fun: dict, num_states: dict, v_index: dict, monitor: BaseMonitor | None = None, system_solver=None):
+        if v_ode.x.array_ro.size != markers.x.array_ro.size:
+            raise RuntimeError("Marker and voltage need to be in the same function space")  # odesolver.py:241-242
+        if v_ode.x.array_ro.size != v_pde.x.array_ro.size:
+            raise NotImplementedError("v_ode and v_pde must be the same P1 space (identity projection, utils.py:52-54)")
+        make = system_solver or ODESystemSolver
+        self.v_ode, self.v_pde, self.markers = v_ode, v_pde, markers
+        self.init_states, self.parameters, self.fun = init_states, parameters, fun
+        self.num_states, self.v_index = dict(num_states), {m: int(v_index[m]) for m in init_states}
+        self.monitor = monitor or NullMonitor()
+        self._marker_values = tuple(init_states.keys())
+        marr = np.asarray(markers.x.array_ro)
+        self._inds = {m: np.nonzero(marr == m)[0] for m in self._marker_values}
+        if sum(len(w) for w in self._inds.values()) != marr.size:
+            raise ValueError("every dof needs a marker that has a cell model")
+        self._odes = {}
+        for m in self._marker_values:
+            shape = (int(num_states[m]), len(self._inds[m]))
+            init = np.asarray(init_states[m], dtype=np.float64)
+            values = np.array(init, order="C") if init.shape == shape else np.repeat(init.reshape(shape[0], 1), shape[1], axis=1)
+            self._odes[m] = make(fun=fun[m], states=values, parameters=parameters[m], monitor=self.monitor, v_index=self.v_index[m])
+        self._pde = getattr(v_pde, "_owner", None)
+
+    # ---- the five hand-offs of the ODESolver protocol ---------------------------------------------------------------
+    def step(self, t0: float, dt: float) -> None:
+        with self.monitor.track_time("total_ode_step"):
+            for m, ode in self._odes.items():
+                with self.monitor.track_time(f"marker_{m}_ode_step"):
+                    ode.step(t0=t0, dt=dt)
+
+    def to_dolfin(self) -> None:  # states[v_index] -> v_ode, region by region
+        arr = self.v_ode.x.array
+        for m, ode in self._odes.items():
+            arr[self._inds[m]] = ode.state_row(self.v_index[m])
+
+    def from_dolfin(self) -> None:  # v_ode -> states[v_index]
+        arr = self.v_ode.x.array_ro
+        for m, ode in self._odes.items():
+            ode.set_state_row(self.v_index[m], arr[self._inds[m]])
+
+    def ode_to_pde(self) -> None:  # identity projection between the two P1 functions, on the host mirrors
+        self.v_pde.x.array[:] = self.v_ode.x.array_ro
+
+    def pde_to_ode(self) -> None:
+        self.v_ode.x.array[:] = self.v_pde.x.array_ro
+
+    # ---- reference surface with a marker argument (odesolver.py:292-303) ----------------------------------------------
+    def values(self, marker: int) -> np.ndarray:
+        return self._odes[marker].states
+
+    def num_parameters(self, marker: int) -> int:
+        return len(self.parameters[marker])
+
+    def shape(self, marker: int) -> tuple[int, int]:
+        return (self.num_states[marker], len(self._inds[marker]))
+
+    def num_points(self, marker: int) -> int:
+        return len(self._inds[marker])
+
+    @property
+    def full_values(self) -> np.ndarray:
+        sizes = set(self.num_states.values())
+        if len(sizes) != 1:
+            raise RuntimeError(f"Cannot get full values since states are not of equal size. Have {self.num_states=}, "
+                               "use .values(marker) instead")
+        out = np.zeros((sizes.pop(), self.markers.x.array_ro.size))
+        for m, ode in self._odes.items():
+            out[:, self._inds[m]] = ode.states
+        return out
+
+    def assign_all_states(self, functions: list[fem.Function]) -> None:
+        n = self.num_states[self._marker_values[0]]
+        assert len(functions) == n, "Number of functions must match number of states"
+        for index, f in enumerate(functions):
+            for m, ode in self._odes.items():
+                f.x.array[self._inds[m]] = ode.states[index, :]
+
+    def states_to_dolfin(self, names: list[str] | None = None) -> list[fem.Function]:
+        n = self.num_states[self._marker_values[0]]
+        if names is not None:
+            assert len(names) == n, f"Number of names must match number of states, got {len(names)} names, but number of states is {n}"
+        else:
+            names = [f"state_{i}" for i in range(n)]
+        functions = [fem.Function(self.v_ode.function_space, name=name) for name in names]
+        self.assign_all_states(functions)
+        return functions

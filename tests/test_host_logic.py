@@ -370,3 +370,95 @@ def test_bench_workload_description_is_the_same_in_both_arms():
         assert abs(L / dx - round(L / dx)) < 1e-9                 # a whole number of elements
     assert bench.cpu_sample_length(0.2) == 20.0                   # small slabs are timed whole
     assert bench.cpu_sample_length(0.025) >= 1.25 - 1e-9          # ... large ones on a block of >= 16 elements incl. the stimulus corner
+
+
+def test_mixed_model_multi_ode_solver_protocol_with_a_stand_in_device_stage():
+    """DolfinMultiODESolver with DIFFERENT cell models per region (src/beat/odesolver.py:228-354 allows any callable per marker)
+    dispatches to MixedModelODESolver: one device ODE stage per region, membrane potential exchanged through the host mirrors.
+    The composite's bookkeeping (region index sets, broadcast of initial states, the five hand-offs, the reference's accessors)
+    is checked here with a NumPy stand-in for the device stage (the oracle's models); on a GPU the stage is ODESystemSolver."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _problems as P
+    from beat_b200 import odesolver
+    from beat_b200.models import fhn, tp06
+
+    oracle = {"fhn": P.oracle_model("fhn"), "tp06": P.oracle_model("tp06")}
+
+    class StandIn:  # what MixedModelODESolver needs from ODESystemSolver
+        def __init__(self, fun, states, parameters, monitor=None, v_index=0):
+            self.fun, self.states, self.parameters = fun, np.array(states), parameters
+            self.step_fn = getattr(oracle[fun.model_tag], "generalized_rush_larsen" if fun.scheme_id == 1 else "forward_explicit_euler")
+
+        def step(self, t0, dt):
+            self.states[:] = self.step_fn(self.states, t0, dt, np.asarray(self.parameters))
+
+        def state_row(self, i):
+            return self.states[i].copy()
+
+        def set_state_row(self, i, v):
+            self.states[i] = v
+
+    mesh = fem.create_unit_square(fem.COMM_SELF, 5, 4)
+    V = fem.functionspace(mesh, ("P", 1))
+    markers = fem.Function(V)
+    markers.x.array[:] = np.where(mesh.geometry.x[:, 0] < 0.45, 7, 3)
+    marr = np.asarray(markers.x.array_ro)
+    v_ode, v_pde = fem.Function(V), fem.Function(V)
+    y = {7: fhn.init_state_values(), 3: tp06.init_state_values(V=-80.0)}
+    p = {7: fhn.init_parameter_values(), 3: tp06.init_parameter_values()}
+    fun = {7: fhn.forward_explicit_euler, 3: tp06.generalized_rush_larsen}
+    vi = {7: fhn.state_index("v"), 3: tp06.state_index("V")}
+    ode = odesolver.DolfinMultiODESolver(v_ode=v_ode, v_pde=v_pde, markers=markers, init_states=y, parameters=p, fun=fun,
+                                         num_states={7: 2, 3: 19}, v_index=vi, system_solver=StandIn)
+    assert isinstance(ode, odesolver.MixedModelODESolver)
+    assert ode.num_points(7) == int((marr == 7).sum()) and ode.shape(3) == (19, int((marr == 3).sum())) and ode.num_parameters(3) == len(p[3])
+    assert np.allclose(ode.values(3), np.asarray(y[3])[:, None]) and np.allclose(ode.values(7), np.asarray(y[7])[:, None])
+    want = {k: np.repeat(np.asarray(y[k])[:, None], ode.num_points(k), axis=1) for k in (7, 3)}
+    t = 0.0
+    for _ in range(3):
+        ode.step(t, 0.02)
+        want[7] = oracle["fhn"].forward_explicit_euler(want[7], t, 0.02, p[7])
+        want[3] = oracle["tp06"].generalized_rush_larsen(want[3], t, 0.02, p[3])
+        t += 0.02
+    for k in (7, 3):
+        assert np.array_equal(ode.values(k), want[k])
+    ode.to_dolfin()
+    assert np.array_equal(v_ode.x.array_ro[marr == 7], want[7][vi[7]]) and np.array_equal(v_ode.x.array_ro[marr == 3], want[3][vi[3]])
+    ode.ode_to_pde()
+    assert np.array_equal(v_pde.x.array_ro, v_ode.x.array_ro)
+    ramp = np.arange(marr.size, dtype=float) + 0.25
+    v_pde.x.array[:] = ramp
+    ode.pde_to_ode()
+    ode.from_dolfin()
+    assert np.array_equal(ode.values(3)[vi[3]], ramp[marr == 3])
+    assert np.array_equal(ode.values(7)[vi[7]], ramp[marr == 7])
+    assert np.array_equal(ode.values(3)[0], want[3][0])  # the other states are untouched
+    with pytest.raises(RuntimeError, match="equal size"):
+        ode.full_values
+    # the splitting solver drives it through the protocol sequence (not the fused device step)
+    calls = []
+
+    class Pde:
+        state = v_pde
+        monitor = telemetry.NullMonitor()
+        parameters = {"theta": 0.5}
+
+        def assign_previous(self):
+            calls.append("assign_previous")
+
+        def step(self, interval):
+            calls.append("pde_step")
+
+    from beat_b200.monodomain_solver import MonodomainSplittingSolver
+
+    solver = MonodomainSplittingSolver.__new__(MonodomainSplittingSolver)
+    solver.pde, solver.ode, solver.theta, solver.monitor = Pde(), ode, 1.0, telemetry.NullMonitor()
+    solver.__post_init__()
+    assert solver._fused is False
+    solver.step((0.0, 0.01))
+    assert calls == ["assign_previous", "assign_previous", "pde_step", "assign_previous"]
+    # same models in every region still take the single-launch path (refused here only because there is no GPU context)
+    same = {7: tp06.generalized_rush_larsen, 3: tp06.generalized_rush_larsen}
+    assert odesolver.DolfinMultiODESolver.__new__(odesolver.DolfinMultiODESolver, v_ode=v_ode, v_pde=v_pde, markers=markers,
+                                                  init_states=y, parameters=p, fun=same, num_states={7: 19, 3: 19},
+                                                  v_index={7: 17, 3: 17}).__class__ is odesolver.DolfinMultiODESolver
